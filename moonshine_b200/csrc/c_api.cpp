@@ -1,0 +1,484 @@
+// extern "C" surface: the reference's transcription ABI (core/moonshine-c-api.h)
+// served by the B200 runtime, plus additive batched / device entry points.
+// Error model as in the reference: nothing throws across the boundary, every
+// failure is logged and mapped to a negative code; loaders return the code as
+// the handle (core/moonshine-c-api.cpp:249-300).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+
+#include "../../include/moonshine_b200.h"
+#include "transcriber.h"
+
+using namespace msb;
+
+namespace {
+
+std::mutex g_map_mutex;
+std::map<int32_t, Transcriber*> g_transcribers;
+int32_t g_next_handle = 0;
+bool g_log_api_calls = false;
+
+std::string to_lower(const std::string& s) {
+  std::string r = s;
+  std::transform(r.begin(), r.end(), r.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+  return r;
+}
+bool bool_from_string(const std::string& v) {
+  const std::string s = to_lower(v);
+  if (s == "true" || s == "1") return true;   // same accepted spellings as the reference
+  if (s == "false" || s == "0") return false;
+  throw std::runtime_error("Invalid boolean string: '" + v + "'");
+}
+float float_from_string(const std::string& v) {
+  size_t pos = 0;
+  float f = std::stof(v, &pos);
+  return f;
+}
+int32_t int_from_string(const std::string& v) { return (int32_t)std::stol(v); }
+
+// Same key set as parse_transcriber_options (core/moonshine-c-api.cpp:129-198);
+// unknown names throw, which fails the load.
+void parse_options(const moonshine_option_t* options, uint64_t count, TranscriberOptions& out) {
+  for (uint64_t i = 0; i < count; i++) {
+    if (options[i].name == nullptr) throw std::runtime_error("Option name is null");
+    const std::string name = to_lower(options[i].name);
+    const std::string value = options[i].value ? options[i].value : "";
+    if (name == "log_api_calls") g_log_api_calls = bool_from_string(value);
+    else if (name == "skip_transcription") out.skip_transcription = true;
+    else if (name == "transcription_interval") out.transcription_interval = float_from_string(value);
+    else if (name == "vad_threshold") out.vad_threshold = float_from_string(value);
+    else if (name == "vad_window_duration") out.vad_window_duration = float_from_string(value);
+    else if (name == "vad_hop_size") out.vad_hop_size = int_from_string(value);
+    else if (name == "vad_look_behind_sample_count") out.vad_look_behind_sample_count = (size_t)std::stoull(value);
+    else if (name == "vad_max_segment_duration") out.vad_max_segment_duration = float_from_string(value);
+    else if (name == "max_tokens_per_second") out.max_tokens_per_second = float_from_string(value);
+    else if (name == "decode_incomplete_lines") out.decode_incomplete_lines = bool_from_string(value);
+    else if (name == "return_audio_data") out.return_audio_data = bool_from_string(value);
+    else if (name == "log_output_text") out.log_output_text = bool_from_string(value);
+    else if (name == "word_timestamps") out.word_timestamps = bool_from_string(value);
+    else if (name == "identify_speakers") out.identify_speakers = bool_from_string(value);
+    else if (name == "keyterms") { if (!value.empty()) out.keyterms.push_back(value); }
+    else if (name == "context") out.context = value;
+    else if (name == "device") out.device = int_from_string(value);  // additive
+    // accepted for compatibility, no effect on this runtime (ORT / CPU-side features)
+    else if (name == "save_input_wav_path" || name == "log_ort_run" || name == "use_speculative_decoding" ||
+             name == "keyterm_boost" || name == "context_max_terms" || name == "diarization_cluster_cadence" ||
+             name == "diarization_analyze_cadence" || name == "diarization_cluster_window_sec" ||
+             name == "diarization_model_dir" || name == "spelling_model_path" || name == "ort_providers" ||
+             name == "ort_provider" || name == "coreml_cache_dir") {}
+    else throw std::runtime_error("Unknown transcriber option: '" + name + "', value=" + value);
+  }
+  if (out.identify_speakers) throw std::runtime_error("identify_speakers is not supported by moonshine-b200");
+  if (out.word_timestamps) {
+    MSB_LOGF("word_timestamps is accepted but not produced by moonshine-b200 yet (words stay NULL)");
+  }
+}
+
+bool is_streaming_arch(uint32_t arch) {
+  return arch == MOONSHINE_MODEL_ARCH_TINY_STREAMING || arch == MOONSHINE_MODEL_ARCH_BASE_STREAMING ||
+         arch == MOONSHINE_MODEL_ARCH_SMALL_STREAMING || arch == MOONSHINE_MODEL_ARCH_MEDIUM_STREAMING;
+}
+
+int32_t register_transcriber(Transcriber* t) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  const int32_t h = g_next_handle++;
+  g_transcribers[h] = t;
+  return h;
+}
+
+Transcriber* lookup(int32_t handle) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (handle < 0) return nullptr;
+  auto it = g_transcribers.find(handle);
+  return it == g_transcribers.end() ? nullptr : it->second;
+}
+
+#define CHECK_HANDLE(t, handle)                                                \
+  Transcriber* t = lookup(handle);                                             \
+  if (t == nullptr) {                                                          \
+    MSB_LOGF("Moonshine transcriber handle is invalid: handle %d", handle);    \
+    return MOONSHINE_ERROR_INVALID_HANDLE;                                     \
+  }
+
+// Canonical asset names the reference accepts as in-memory keys
+// (c-api.h:497-516) plus this runtime's weight container.
+const std::set<std::string>& known_memory_keys() {
+  static const std::set<std::string> k = {
+      "encoder_model.ort", "decoder_model_merged.ort", "tokenizer.bin", "decoder_with_attention.ort",
+      "alignment_model.ort", "frontend.ort", "encoder.ort", "adapter.ort", "cross_kv.ort",
+      "decoder_kv.ort", "streaming_config.json", "decoder_kv_with_attention.ort", "spelling_cnn.ort",
+      "segmentation.ort", "embedding.ort", "model.msw"};
+  return k;
+}
+
+std::string basename_of(const std::string& p) {
+  const size_t pos = p.find_last_of('/');
+  return pos == std::string::npos ? p : p.substr(pos + 1);
+}
+
+std::vector<uint8_t> read_file(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("Failed to open '" + path + "'");
+  std::fseek(f, 0, SEEK_END);
+  long sz = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)std::max<long>(sz, 0));
+  if (sz > 0 && std::fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) {
+    std::fclose(f);
+    throw std::runtime_error("Failed to read '" + path + "'");
+  }
+  std::fclose(f);
+  return buf;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t moonshine_get_version(void) { return MOONSHINE_HEADER_VERSION; }
+
+const char* moonshine_error_to_string(int32_t error) {
+  if (error == MOONSHINE_ERROR_NONE) return "Success";
+  if (error == MOONSHINE_ERROR_INVALID_HANDLE) return "Invalid handle";
+  if (error == MOONSHINE_ERROR_INVALID_ARGUMENT) return "Invalid argument";
+  return "Unknown error";
+}
+
+void moonshine_free_buffer(void* ptr) { std::free(ptr); }
+
+int32_t moonshine_load_transcriber_from_files(const char* path, uint32_t model_arch,
+                                              const moonshine_option_t* options,
+                                              uint64_t options_count, int32_t moonshine_version) {
+  (void)moonshine_version;
+  Transcriber* t = nullptr;
+  try {
+    TranscriberOptions opts;
+    parse_options(options, options_count, opts);
+    if (g_log_api_calls) MSB_LOGF("moonshine_load_transcriber_from_files(path=%s, model_arch=%u)", path ? path : "(null)", model_arch);
+    if (!opts.skip_transcription) {
+      if (is_streaming_arch(model_arch)) {
+        throw std::runtime_error("Streaming model architectures are not implemented by moonshine-b200 yet");
+      }
+      dims_for_arch(model_arch);  // validates
+      if (path == nullptr) throw std::runtime_error("Model path is null");
+    }
+    t = new Transcriber(opts, model_arch);
+    if (!opts.skip_transcription) t->load_from_directory(path);
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to load transcriber: %s", e.what());
+    delete t;
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return register_transcriber(t);
+}
+
+int32_t moonshine_load_transcriber_from_memory(const uint8_t*, size_t, const uint8_t*, size_t,
+                                               const uint8_t*, size_t, const uint8_t*, size_t,
+                                               uint32_t, const moonshine_option_t*, uint64_t,
+                                               int32_t moonshine_version) {
+  if (moonshine_version >= MOONSHINE_FROM_MEMORY_REMOVED_VERSION) {
+    MSB_LOGF("moonshine_load_transcriber_from_memory is no longer supported for header version %d; "
+             "use moonshine_load_transcriber_from_memory_files", moonshine_version);
+    return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  }
+  MSB_LOGF("moonshine_load_transcriber_from_memory takes ONNX Runtime graph bytes, which moonshine-b200 "
+           "cannot execute; pass model.msw through moonshine_load_transcriber_from_memory_files");
+  return MOONSHINE_ERROR_UNKNOWN;
+}
+
+int32_t moonshine_load_transcriber_from_memory_files(const char** filenames, const uint8_t** memory,
+                                                     const uint64_t* memory_sizes, uint64_t file_count,
+                                                     uint32_t model_arch, const moonshine_option_t* options,
+                                                     uint64_t options_count, int32_t moonshine_version) {
+  (void)moonshine_version;
+  Transcriber* t = nullptr;
+  try {
+    TranscriberOptions opts;
+    parse_options(options, options_count, opts);
+    if (file_count > 0 && filenames == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+    const uint8_t *wbytes = nullptr, *tbytes = nullptr;
+    size_t wsize = 0, tsize = 0;
+    std::vector<uint8_t> wfile, tfile;
+    for (uint64_t i = 0; i < file_count; i++) {
+      if (filenames[i] == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+      const std::string key = basename_of(filenames[i]);
+      if (!known_memory_keys().count(key)) {
+        MSB_LOGF("Unrecognized in-memory model file key '%s'", filenames[i]);
+        return MOONSHINE_ERROR_INVALID_ARGUMENT;
+      }
+      const bool in_memory = memory && memory_sizes && memory[i] != nullptr && memory_sizes[i] > 0;
+      if (key == "model.msw") {
+        if (in_memory) { wbytes = memory[i]; wsize = (size_t)memory_sizes[i]; }
+        else { wfile = read_file(filenames[i]); wbytes = wfile.data(); wsize = wfile.size(); }
+      } else if (key == "tokenizer.bin") {
+        if (in_memory) { tbytes = memory[i]; tsize = (size_t)memory_sizes[i]; }
+        else { tfile = read_file(filenames[i]); tbytes = tfile.data(); tsize = tfile.size(); }
+      }
+    }
+    if (!opts.skip_transcription) {
+      if (is_streaming_arch(model_arch)) {
+        throw std::runtime_error("Streaming model architectures are not implemented by moonshine-b200 yet");
+      }
+      dims_for_arch(model_arch);
+      if (wbytes == nullptr) throw std::runtime_error("Missing required asset 'model.msw'");
+      if (tbytes == nullptr) throw std::runtime_error("Missing required asset 'tokenizer.bin'");
+    }
+    t = new Transcriber(opts, model_arch);
+    if (!opts.skip_transcription) t->load_from_memory(wbytes, wsize, tbytes, tsize);
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to load transcriber from memory files: %s", e.what());
+    delete t;
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return register_transcriber(t);
+}
+
+void moonshine_free_transcriber(int32_t transcriber_handle) {
+  Transcriber* t = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_transcribers.find(transcriber_handle);
+    if (it == g_transcribers.end()) return;
+    t = it->second;
+    g_transcribers.erase(it);
+  }
+  delete t;
+}
+
+int32_t moonshine_transcribe_without_streaming(int32_t transcriber_handle, float* audio_data,
+                                               uint64_t audio_length, int32_t sample_rate,
+                                               uint32_t flags, transcript_t** out_transcript) {
+  CHECK_HANDLE(t, transcriber_handle);
+  try {
+    t->transcribe_without_streaming(audio_data, audio_length, sample_rate, flags, out_transcript);
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to transcribe without streaming: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_transcribe_batch_without_streaming(int32_t transcriber_handle, const float* const* audio,
+                                                     const uint64_t* lengths, uint64_t count,
+                                                     int32_t sample_rate, uint32_t flags,
+                                                     transcript_t** out_transcripts) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (count > 0 && (audio == nullptr || lengths == nullptr)) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  try {
+    t->transcribe_batch(audio, lengths, count, sample_rate, flags, out_transcripts);
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to transcribe batch: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_create_stream(int32_t transcriber_handle, uint32_t flags) {
+  (void)flags;
+  CHECK_HANDLE(t, transcriber_handle);
+  try {
+    return t->create_stream();
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to create stream: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+}
+
+#define STREAM_CALL(expr, desc)                          \
+  CHECK_HANDLE(t, transcriber_handle);                   \
+  try {                                                  \
+    expr;                                                \
+  } catch (const std::exception& e) {                    \
+    MSB_LOGF("Failed to " desc ": %s", e.what());        \
+    return MOONSHINE_ERROR_UNKNOWN;                      \
+  }                                                      \
+  return MOONSHINE_ERROR_NONE;
+
+int32_t moonshine_free_stream(int32_t transcriber_handle, int32_t stream_handle) {
+  STREAM_CALL(t->free_stream(stream_handle), "free stream")
+}
+int32_t moonshine_start_stream(int32_t transcriber_handle, int32_t stream_handle) {
+  STREAM_CALL(t->start_stream(stream_handle), "start stream")
+}
+int32_t moonshine_stop_stream(int32_t transcriber_handle, int32_t stream_handle) {
+  STREAM_CALL(t->stop_stream(stream_handle), "stop stream")
+}
+int32_t moonshine_transcribe_add_audio_to_stream(int32_t transcriber_handle, int32_t stream_handle,
+                                                 const float* new_audio_data, uint64_t audio_length,
+                                                 int32_t sample_rate, uint32_t flags) {
+  (void)flags;
+  STREAM_CALL(t->add_audio_to_stream(stream_handle, new_audio_data, audio_length, sample_rate),
+              "add audio to stream")
+}
+int32_t moonshine_transcribe_stream(int32_t transcriber_handle, int32_t stream_handle, uint32_t flags,
+                                    transcript_t** out_transcript) {
+  STREAM_CALL(t->transcribe_stream(stream_handle, flags, out_transcript), "transcribe stream")
+}
+
+int32_t moonshine_transcriber_set_keyterms(int32_t transcriber_handle, const char*) {
+  CHECK_HANDLE(t, transcriber_handle);
+  (void)t;
+  MSB_LOGF("Failed to set keyterms: only the streaming architectures decode through a path that can apply the bias");
+  return MOONSHINE_ERROR_UNKNOWN;
+}
+int32_t moonshine_transcriber_set_context(int32_t transcriber_handle, const char*, int32_t) {
+  CHECK_HANDLE(t, transcriber_handle);
+  (void)t;
+  MSB_LOGF("Failed to set context: only the streaming architectures decode through a path that can apply the bias");
+  return MOONSHINE_ERROR_UNKNOWN;
+}
+
+const char* moonshine_transcript_to_string(const transcript_t* transcript) {
+  static std::string description;  // process-static, like the reference
+  std::string r;
+  if (transcript == nullptr) {
+    description = "0 lines\n";
+    return description.c_str();
+  }
+  r += std::to_string(transcript->line_count) + " lines\n";
+  for (uint64_t i = 0; i < transcript->line_count; i++) {
+    const transcript_line_t& line = transcript->lines[i];
+    char ts[32];
+    snprintf(ts, sizeof(ts), "%.1fs: ", line.start_time);
+    r += ts;
+    r += line.text == nullptr ? std::string("<null>") : std::string(line.text);
+    r += "\n";
+  }
+  description = r;
+  return description.c_str();
+}
+
+// ---- additive: device path, timing, parity hooks ----
+int32_t moonshine_b200_transcribe_device(int32_t transcriber_handle, const float* d_pcm, int64_t stride,
+                                         const uint64_t* lengths, uint64_t count, int32_t* out_tokens,
+                                         int32_t out_stride, int32_t* out_counts) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr || d_pcm == nullptr || lengths == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  try {
+    std::lock_guard<std::mutex> lock(t->model_mutex());
+    std::vector<std::vector<int32_t>> tokens;
+    t->model()->transcribe_device(d_pcm, stride, lengths, (int)count, t->options().max_tokens_per_second, tokens);
+    for (uint64_t i = 0; i < count; i++) {
+      const int n = (int)std::min<size_t>(tokens[i].size(), (size_t)std::max(out_stride, 0));
+      if (out_counts) out_counts[i] = (int32_t)tokens[i].size();
+      if (out_tokens) std::memcpy(out_tokens + (size_t)i * out_stride, tokens[i].data(), n * sizeof(int32_t));
+    }
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to transcribe device batch: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
+void* moonshine_b200_get_stream(int32_t transcriber_handle) {
+  Transcriber* t = lookup(transcriber_handle);
+  if (t == nullptr || t->model() == nullptr) return nullptr;
+  return (void*)t->model()->stream();
+}
+
+int32_t moonshine_b200_set_timing(int32_t transcriber_handle, int32_t enabled) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  t->model()->set_timing(enabled != 0);
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_b200_last_timings(int32_t transcriber_handle, double* out8) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr || out8 == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  const StageTimes& s = t->model()->last_times();
+  out8[0] = s.frontend_ms; out8[1] = s.encoder_ms; out8[2] = s.cross_kv_ms; out8[3] = s.decode_ms;
+  out8[4] = s.decode_steps; out8[5] = s.kernel_launches; out8[6] = (double)t->model()->weight_bytes();
+  out8[7] = 0;
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_b200_debug_run(int32_t transcriber_handle, const float* const* audio,
+                                 const uint64_t* lengths, uint64_t count, float* enc_out,
+                                 uint64_t enc_out_capacity, int32_t* enc_frames, const int32_t* forced,
+                                 int32_t forced_stride, float* logits, int32_t logits_steps,
+                                 int32_t* out_tokens, int32_t out_stride, int32_t* out_counts) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  try {
+    std::lock_guard<std::mutex> lock(t->model_mutex());
+    DebugCapture dbg;
+    std::vector<float> enc, lg;
+    std::vector<int> frames;
+    if (enc_out || enc_frames) { dbg.encoder_out = &enc; dbg.encoder_frames = &frames; }
+    if (logits && logits_steps > 0) { dbg.logits = &lg; dbg.logits_steps = logits_steps; }
+    dbg.forced = forced;
+    dbg.forced_stride = forced_stride;
+    std::vector<std::vector<int32_t>> tokens;
+    t->model()->transcribe(audio, lengths, (int)count, t->options().max_tokens_per_second, tokens, &dbg);
+    if (enc_out) {
+      if (enc.size() > enc_out_capacity) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+      std::memcpy(enc_out, enc.data(), enc.size() * sizeof(float));
+    }
+    if (enc_frames) for (uint64_t i = 0; i < count; i++) enc_frames[i] = frames[i];
+    if (logits) {
+      std::memset(logits, 0, (size_t)logits_steps * count * t->model()->dims().vocab * sizeof(float));
+      std::memcpy(logits, lg.data(), lg.size() * sizeof(float));
+    }
+    for (uint64_t i = 0; i < count; i++) {
+      const int n = (int)std::min<size_t>(tokens[i].size(), (size_t)std::max(out_stride, 0));
+      if (out_counts) out_counts[i] = (int32_t)tokens[i].size();
+      if (out_tokens) std::memcpy(out_tokens + (size_t)i * out_stride, tokens[i].data(), n * sizeof(int32_t));
+    }
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug run failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, int32_t M, int32_t N,
+                                 int32_t K, int32_t lda, int32_t ldw, int32_t ldc, const float* d_bias,
+                                 int32_t act, int32_t accumulate, int32_t impl) {
+  (void)impl;
+  try {
+    GemmParams g;
+    g.A = dA; g.W = dW; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.rs = ldc;
+    g.bias = d_bias; g.act = act; g.accumulate = accumulate;
+    launch_gemm(g, nullptr);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+  } catch (const std::exception& e) {
+    MSB_LOGF("test gemm failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
+// ---- Part 2 stubs: symbols exist so bindings resolve at dlopen; every call
+// reports failure (TTS / G2P / embeddings / catalogs are out of scope). ----
+#define STUB_LOG(name) MSB_LOGF(name " is not implemented by moonshine-b200 (transcription path only)")
+int32_t moonshine_create_embedding_model(const char*, uint32_t, const char*) { STUB_LOG("moonshine_create_embedding_model"); return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_create_embedding_model_from_memory(uint32_t, const char*, const char**, uint64_t, const uint8_t**, const uint64_t*, const moonshine_option_t*, uint64_t, int32_t) { STUB_LOG("moonshine_create_embedding_model_from_memory"); return MOONSHINE_ERROR_UNKNOWN; }
+void moonshine_free_embedding_model(int32_t) {}
+int32_t moonshine_calculate_embedding(int32_t, const char*, float**, uint64_t*, const char*) { return MOONSHINE_ERROR_UNKNOWN; }
+void moonshine_free_embedding(float* e) { std::free(e); }
+int32_t moonshine_calculate_embedding_distance(int32_t, const float*, const float*, uint64_t, float*) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_extract_speech_clip(const float*, uint64_t, int32_t, int32_t, const moonshine_option_t*, uint64_t, moonshine_speech_clip_t*) { STUB_LOG("moonshine_extract_speech_clip"); return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_create_tts_synthesizer_from_files(const char*, const char**, uint64_t, const moonshine_option_t*, uint64_t, int32_t) { STUB_LOG("moonshine_create_tts_synthesizer_from_files"); return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_create_tts_synthesizer_from_memory(const char*, const char**, const uint64_t, const uint8_t**, const uint64_t*, const moonshine_option_t*, uint64_t, int32_t) { STUB_LOG("moonshine_create_tts_synthesizer_from_memory"); return MOONSHINE_ERROR_UNKNOWN; }
+void moonshine_free_tts_synthesizer(int32_t) {}
+int32_t moonshine_get_g2p_dependencies(const char*, const moonshine_option_t*, uint64_t, char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_tts_dependencies(const char*, const moonshine_option_t*, uint64_t, char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_tts_voices(const char*, const moonshine_option_t*, uint64_t, char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_stt_dependencies(const char*, const moonshine_option_t*, uint64_t, char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_embedding_dependencies(const char*, const moonshine_option_t*, uint64_t, char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_diarization_dependencies(char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_stt_catalog(char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_get_embedding_catalog(char**) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_text_to_speech(int32_t, const char*, const moonshine_option_t*, uint64_t, float**, uint64_t*, int32_t*) { STUB_LOG("moonshine_text_to_speech"); return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_phonemes_to_speech(int32_t, const char*, const moonshine_option_t*, uint64_t, float**, uint64_t*, int32_t*) { STUB_LOG("moonshine_phonemes_to_speech"); return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_create_grapheme_to_phonemizer_from_files(const char*, const char**, uint64_t, const moonshine_option_t*, uint64_t, int32_t) { return MOONSHINE_ERROR_UNKNOWN; }
+int32_t moonshine_create_grapheme_to_phonemizer_from_memory(const char*, const char**, const uint64_t, const uint8_t**, const uint64_t*, const moonshine_option_t*, uint64_t, int32_t) { return MOONSHINE_ERROR_UNKNOWN; }
+void moonshine_free_grapheme_to_phonemizer(int32_t) {}
+int32_t moonshine_text_to_phonemes(int32_t, const char*, const moonshine_option_t*, uint64_t, const char**, uint64_t*) { return MOONSHINE_ERROR_UNKNOWN; }
+
+}  // extern "C"

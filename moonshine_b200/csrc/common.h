@@ -1,0 +1,126 @@
+// Shared host-side helpers for the B200 Moonshine runtime.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace msb {
+
+inline std::string format(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+#define MSB_LOGF(...)                                   \
+  do {                                                  \
+    fprintf(stderr, "[moonshine-b200] " __VA_ARGS__);   \
+    fprintf(stderr, "\n");                              \
+  } while (0)
+
+#define CUDA_CHECK(expr)                                                        \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      throw std::runtime_error(msb::format("CUDA error %s at %s:%d: %s",        \
+                                           cudaGetErrorName(_e), __FILE__,      \
+                                           __LINE__, cudaGetErrorString(_e)));  \
+    }                                                                           \
+  } while (0)
+
+// Model dimensions.  TINY/BASE follow core/moonshine-model.cpp:41-79 of the
+// reference (6/8/36 and 8/8/52) plus the HF config the graphs were exported
+// from; 100/101 are reduced-size unit-test configs.
+struct Dims {
+  int arch = 0;
+  int dim = 0;         // D
+  int enc_layers = 0;
+  int dec_layers = 0;
+  int heads = 0;
+  int head_dim = 0;
+  int ffn = 0;         // I
+  int vocab = 32768;
+  int rot_dim = 0;     // rotated dims per head (interleaved pairs)
+  int rope_den = 0;    // int(head_dim * partial_rotary_factor)
+  float rope_theta = 10000.0f;
+  int bos = 1;
+  int eos = 2;
+};
+
+inline Dims dims_for_arch(uint32_t arch) {
+  Dims d;
+  d.arch = (int)arch;
+  auto set = [&](int D, int el, int dl, int H, int hd, int I, int V) {
+    d.dim = D; d.enc_layers = el; d.dec_layers = dl; d.heads = H;
+    d.head_dim = hd; d.ffn = I; d.vocab = V;
+    d.rope_den = (int)((double)hd * 0.9);   // HF: int(head_dim * partial_rotary_factor), in double like Python
+    d.rot_dim = 2 * ((d.rope_den + 1) / 2); // arange(0, dim, 2) frequencies, one pair each
+  };
+  switch (arch) {
+    case 0: set(288, 6, 6, 8, 36, 1152, 32768); break;   // MOONSHINE_MODEL_ARCH_TINY
+    case 1: set(416, 8, 8, 8, 52, 1664, 32768); break;   // MOONSHINE_MODEL_ARCH_BASE
+    case 100: set(64, 2, 2, 4, 16, 96, 512); break;      // unit-test config "test"
+    case 101: set(72, 2, 3, 2, 36, 80, 300); break;      // unit-test config "test2"
+    default:
+      throw std::runtime_error(format("Unsupported model architecture %u", arch));
+  }
+  return d;
+}
+
+// Frame counts of the conv frontend (no padding): k127/s64, k7/s3, k3/s2.
+inline void frontend_lengths(int64_t n, int& t1, int& t2, int& t3) {
+  t1 = n >= 127 ? (int)((n - 127) / 64 + 1) : 0;
+  t2 = t1 >= 7 ? (t1 - 7) / 3 + 1 : 0;
+  t3 = t2 >= 3 ? (t2 - 3) / 2 + 1 : 0;
+}
+
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  // Grow-only allocation.
+  void reserve(size_t n) {
+    if (n <= count) return;
+    release();
+    CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+template <typename T>
+struct PinnedBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  PinnedBuffer() = default;
+  PinnedBuffer(const PinnedBuffer&) = delete;
+  PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+  ~PinnedBuffer() { if (ptr) cudaFreeHost(ptr); }
+  void reserve(size_t n) {
+    if (n <= count) return;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    CUDA_CHECK(cudaMallocHost(&ptr, n * sizeof(T)));
+    count = n;
+  }
+};
+
+}  // namespace msb

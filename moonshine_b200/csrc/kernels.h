@@ -1,0 +1,140 @@
+// Kernel launch interface (host-callable) for the Moonshine B200 runtime.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace msb {
+
+// ---------------------------------------------------------------------------
+// Grouped "NT" GEMM:  C_z[m, n] = epi( alpha * sum_k A_z[m, k] * W_z[n, k] )
+// A rows have stride lda, W rows stride ldw (both K-contiguous, multiples of 4
+// floats, 16-byte aligned bases).  Per-group dims/offsets are optional device
+// arrays; without them group z uses z * stride{A,W,C} and the uniform M/N/K.
+// ---------------------------------------------------------------------------
+struct GemmParams {
+  const float* A = nullptr;
+  const float* W = nullptr;
+  void* C = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0;
+  int groups = 1;
+  int64_t strideA = 0, strideW = 0, strideC = 0;
+  const int64_t* offA = nullptr;
+  const int64_t* offW = nullptr;
+  const int64_t* offC = nullptr;
+  const int* Mz = nullptr;
+  const int* Nz = nullptr;
+  const int* Kz = nullptr;
+  // epilogue
+  float alpha = 1.0f;
+  const float* bias = nullptr;  // indexed by n (or by m when bias_on_m)
+  int bias_on_m = 0;
+  int act = 0;                  // 0 = none, 1 = exact-erf GELU
+  int accumulate = 0;           // C += result (fp32 output only)
+  int out_half = 0;             // store __half instead of float
+  // output addressing: addr = offC + rowoff(m) + coloff(n)
+  //   rowoff(m) = rm1 ? (m / rm1) * rs1 + ((m % rm1) / rm2) * rs2 + (m % rm2) * rs : m * rs
+  //   coloff(n) = cm1 ? (n / cm1) * cs1 + ((n % cm1) / cm2) * cs2 + (n % cm2)      : n
+  int64_t rs = 0;
+  int rm1 = 0, rm2 = 1;
+  int64_t rs1 = 0, rs2 = 0;
+  int cm1 = 0, cm2 = 1;
+  int64_t cs1 = 0, cs2 = 0;
+  // optional interleaved-pair RoPE on columns n < rope_cols (per-row position)
+  const int* pos = nullptr;        // [M]
+  const float* rope_cos = nullptr; // [max_pos][rot_dim / 2]
+  const float* rope_sin = nullptr;
+  int rope_cols = 0, head_dim = 1, rot_dim = 0;
+};
+void launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Frontend
+// ---------------------------------------------------------------------------
+// conv1 (1 -> D, k=127, s=64, no bias) + tanh, channel-last output rows
+// off1[b] + t, plus per-utterance GroupNorm(1 group) statistics.
+void launch_conv1_tanh(const float* pcm, int64_t pcm_stride, const int* n_samples, const int* t1,
+                       const int64_t* off1, const float* w1t /*[127][D]*/, float* h1, int D,
+                       int B, int max_t1, double* gn_partial /*[B][nblk][2]*/, int* nblk_out,
+                       cudaStream_t stream);
+int conv1_blocks_per_utt(int max_t1);
+// (x - mean) * rstd * gamma[c] + beta[c], in place, using the partial sums.
+void launch_groupnorm_apply(float* h1, const int* t1, const int64_t* off1, const double* gn_partial,
+                            int nblk, const float* gamma, const float* beta, int D, int B,
+                            int max_t1, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Row-wise ops
+// ---------------------------------------------------------------------------
+// y = (x - mean) / sqrt(var + 1e-5) * gamma   (nn.LayerNorm(D, bias=False))
+void launch_layernorm(const float* x, float* y, const float* gamma, int64_t rows, int D,
+                      cudaStream_t stream);
+// In-place softmax over the first n_z columns of each row of group z's
+// [m_z, ld] score matrix; columns [n_z, ld) are zeroed.
+void launch_softmax_rows(float* S, const int64_t* offS, const int* Mz, const int* Nz, int ld,
+                         int groups, int max_m, cudaStream_t stream);
+void launch_gelu_inplace(float* x, int64_t n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Decoder (persistent, one launch per greedy token)
+// ---------------------------------------------------------------------------
+struct DecLayerWeights {
+  const float* ln1;    // [D]
+  const float* wqkv;   // [H][D][3*hd]  k-major per head: (q | k | v) columns
+  const float* wo;     // [H][hd][D]    rows of o_proj^T belonging to head h
+  const float* ln2;
+  const float* wqc;    // [H][D][hd]
+  const float* woc;    // [H][hd][D]
+  const float* ln3;
+  const float* w1;     // [n_chunk][D][2*IC]  (up | gate) columns of the chunk
+  const float* b1;     // [n_chunk][2*IC]
+  const float* w2;     // [n_chunk][IC][D]
+  const float* b2;     // [D]
+};
+
+constexpr int kMaxDecLayers = 8;
+
+struct DecoderParams {
+  int B, D, H, hd, I, V, L, rot_dim;
+  int step;               // decode position of the token being consumed
+  int Tpad;               // cross K/V time padding (multiple of 8)
+  int Smax;               // self K/V capacity (positions)
+  int IC;                 // FFN columns per MLP work item (divides I)
+  int n_chunk;            // I / IC
+  int n_vchunk;           // vocab chunks in the logits phase
+  int vchunk;             // vocab entries per chunk
+  DecLayerWeights layers[kMaxDecLayers];
+  const float* embed;     // [V][D]   (gather)
+  const float* embT;      // [D][V]   (tied logits head, k-major)
+  const float* final_ln;  // [D]
+  const float* rope_cos;  // [Smax][rot/2]
+  const float* rope_sin;
+  const int* enc_len;     // [B] cross length T_b
+  const int* max_len;     // [B] max decode steps per utterance
+  const __half* kc;       // [L][B][H][hd][Tpad]   cross K, d-major
+  const __half* vc;       // [L][B][H][Tpad][hd]   cross V
+  float* ks;              // [L][B][H][hd][Smax]   self K, d-major
+  float* vs;              // [L][B][H][Smax][hd]   self V
+  float* hbuf;            // [2][B][D]  residual stream (ping-pong)
+  float* part;            // [2H + n_chunk][B][D] partial sums (A | B | C)
+  float* xfin;            // [B][D] final-LN rows feeding the logits phase
+  float* cand_val;        // [2][n_vchunk][B]  per-chunk argmax candidates (ping-pong by step parity)
+  int* cand_idx;          // [2][n_vchunk][B]
+  int* tokens;            // [B][Smax + 1] emitted ids (index 0 = start token)
+  int* n_tokens;          // [B] ids emitted so far (incl. start token)
+  int* done;              // [B]
+  int* n_active;          // [1] utterances still decoding (updated at step start)
+  float* logits_out;      // optional [B][V] dump of this step's logits (parity/debug)
+  const int* forced;      // optional [B][Smax + 1] teacher-forced ids
+  unsigned int* barrier;  // [2] grid barrier state
+};
+void launch_decoder_step(const DecoderParams& p, int grid, cudaStream_t stream);
+void decoder_tiles_for_batch(int B, int& nb_attn, int& nb_mlp);
+size_t decoder_step_smem_bytes(const DecoderParams& p);
+// Resolves the last step's argmax into tokens[] (the step kernel resolves the
+// previous step's candidates in its prologue).
+void launch_decoder_finalize(const DecoderParams& p, cudaStream_t stream);
+
+}  // namespace msb

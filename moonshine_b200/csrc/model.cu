@@ -1,0 +1,623 @@
+// Host orchestration of the batched encoder and the greedy decoder.
+#include "model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace msb {
+
+namespace {
+
+// Appends tensors to one host blob (256-byte aligned) that is uploaded once.
+struct BlobBuilder {
+  std::vector<float> data;
+  size_t add(size_t count) {
+    size_t off = (data.size() + 63) / 64 * 64;
+    data.resize(off + count, 0.f);
+    return off;
+  }
+  size_t add_copy(const float* src, size_t count) {
+    size_t off = add(count);
+    std::memcpy(data.data() + off, src, count * sizeof(float));
+    return off;
+  }
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+int Model::max_len_for(uint64_t n_samples, float max_tokens_per_second) {
+  // `const float audio_duration = size / 16000.0f; ceil(duration * tps)`
+  const float audio_duration = (float)n_samples / 16000.0f;
+  return (int)std::ceil(audio_duration * max_tokens_per_second);
+}
+
+Model::Model(const Dims& dims, const WeightFile& weights, int device) : d_(dims), device_(device) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10) {
+    throw std::runtime_error(format("moonshine-b200 requires an sm_100a GPU, found sm_%d%d (%s)",
+                                    prop.major, prop.minor, prop.name));
+  }
+  sm_count_ = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (auto& e : ev_) CUDA_CHECK(cudaEventCreate(&e));
+  if (d_.dec_layers > kMaxDecLayers) throw std::runtime_error("too many decoder layers");
+  build_weights(weights);
+  barrier_.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(barrier_.ptr, 0, 2 * sizeof(unsigned), stream_));
+  nactive_.reserve(1);
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+Model::~Model() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Model::build_weights(const WeightFile& wf) {
+  const int D = d_.dim, I = d_.ffn, H = d_.heads, hd = d_.head_dim, V = d_.vocab;
+  if (H * hd != D) throw std::runtime_error("heads * head_dim must equal the hidden size");
+  if (D % 4 || hd % 4 || I % 4) throw std::runtime_error("dims must be multiples of 4");
+  ffn_chunk_ = (I % 64 == 0) ? 64 : (I % 32 == 0) ? 32 : 16;
+  if (I % ffn_chunk_) throw std::runtime_error("ffn size must be a multiple of 16");
+  const int IC = ffn_chunk_, n_chunk = I / IC;
+
+  BlobBuilder bb;
+  const std::string e = "model.encoder.";
+  // conv1 [D][1][127] -> [127][D]
+  size_t o_w1t = bb.add((size_t)127 * D);
+  {
+    const float* w = wf.get(e + "conv1.weight", {D, 1, 127}).data;
+    for (int c = 0; c < D; c++)
+      for (int j = 0; j < 127; j++) bb.data[o_w1t + (size_t)j * D + c] = w[(size_t)c * 127 + j];
+  }
+  size_t o_gnw = bb.add_copy(wf.get(e + "groupnorm.weight", {D}).data, D);
+  size_t o_gnb = bb.add_copy(wf.get(e + "groupnorm.bias", {D}).data, D);
+  // conv2 [2D][D][7] -> [2D][7*D] with K index = k*D + c (channel-last windows)
+  size_t o_c2 = bb.add((size_t)2 * D * 7 * D);
+  {
+    const float* w = wf.get(e + "conv2.weight", {2 * D, D, 7}).data;
+    for (int o = 0; o < 2 * D; o++)
+      for (int c = 0; c < D; c++)
+        for (int k = 0; k < 7; k++)
+          bb.data[o_c2 + ((size_t)o * 7 + k) * D + c] = w[((size_t)o * D + c) * 7 + k];
+  }
+  size_t o_c2b = bb.add_copy(wf.get(e + "conv2.bias", {2 * D}).data, 2 * D);
+  size_t o_c3 = bb.add((size_t)D * 3 * 2 * D);
+  {
+    const float* w = wf.get(e + "conv3.weight", {D, 2 * D, 3}).data;
+    for (int o = 0; o < D; o++)
+      for (int c = 0; c < 2 * D; c++)
+        for (int k = 0; k < 3; k++)
+          bb.data[o_c3 + ((size_t)o * 3 + k) * 2 * D + c] = w[((size_t)o * 2 * D + c) * 3 + k];
+  }
+  size_t o_c3b = bb.add_copy(wf.get(e + "conv3.bias", {D}).data, D);
+
+  struct EncOff { size_t ln1, wqk, wv, wo, ln2, w1, b1, w2, b2; };
+  std::vector<EncOff> eo(d_.enc_layers);
+  for (int l = 0; l < d_.enc_layers; l++) {
+    const std::string p = e + "layers." + std::to_string(l) + ".";
+    eo[l].ln1 = bb.add_copy(wf.get(p + "input_layernorm.weight", {D}).data, D);
+    eo[l].wqk = bb.add((size_t)2 * D * D);
+    std::memcpy(&bb.data[eo[l].wqk], wf.get(p + "self_attn.q_proj.weight", {D, D}).data, sizeof(float) * D * D);
+    std::memcpy(&bb.data[eo[l].wqk + (size_t)D * D], wf.get(p + "self_attn.k_proj.weight", {D, D}).data, sizeof(float) * D * D);
+    eo[l].wv = bb.add_copy(wf.get(p + "self_attn.v_proj.weight", {D, D}).data, (size_t)D * D);
+    eo[l].wo = bb.add_copy(wf.get(p + "self_attn.o_proj.weight", {D, D}).data, (size_t)D * D);
+    eo[l].ln2 = bb.add_copy(wf.get(p + "post_attention_layernorm.weight", {D}).data, D);
+    eo[l].w1 = bb.add_copy(wf.get(p + "mlp.fc1.weight", {I, D}).data, (size_t)I * D);
+    eo[l].b1 = bb.add_copy(wf.get(p + "mlp.fc1.bias", {I}).data, I);
+    eo[l].w2 = bb.add_copy(wf.get(p + "mlp.fc2.weight", {D, I}).data, (size_t)D * I);
+    eo[l].b2 = bb.add_copy(wf.get(p + "mlp.fc2.bias", {D}).data, D);
+  }
+  size_t o_encln = bb.add_copy(wf.get(e + "layer_norm.weight", {D}).data, D);
+
+  // ---- decoder ----
+  const std::string dd = "model.decoder.";
+  const float* emb = wf.get(dd + "embed_tokens.weight", {V, D}).data;
+  size_t o_emb = bb.add_copy(emb, (size_t)V * D);
+  size_t o_embT = bb.add((size_t)D * V);
+  for (int v = 0; v < V; v++)
+    for (int k = 0; k < D; k++) bb.data[o_embT + (size_t)k * V + v] = emb[(size_t)v * D + k];
+  size_t o_decln = bb.add_copy(wf.get(dd + "norm.weight", {D}).data, D);
+  size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
+  size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
+  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2; };
+  std::vector<DecOff> dof(d_.dec_layers);
+  for (int l = 0; l < d_.dec_layers; l++) {
+    const std::string p = dd + "layers." + std::to_string(l) + ".";
+    const float* q = wf.get(p + "self_attn.q_proj.weight", {D, D}).data;
+    const float* k = wf.get(p + "self_attn.k_proj.weight", {D, D}).data;
+    const float* v = wf.get(p + "self_attn.v_proj.weight", {D, D}).data;
+    const float* o = wf.get(p + "self_attn.o_proj.weight", {D, D}).data;
+    const float* qc = wf.get(p + "encoder_attn.q_proj.weight", {D, D}).data;
+    const float* kc = wf.get(p + "encoder_attn.k_proj.weight", {D, D}).data;
+    const float* vc = wf.get(p + "encoder_attn.v_proj.weight", {D, D}).data;
+    const float* oc = wf.get(p + "encoder_attn.o_proj.weight", {D, D}).data;
+    const float* f1 = wf.get(p + "mlp.fc1.weight", {2 * I, D}).data;
+    const float* f1b = wf.get(p + "mlp.fc1.bias", {2 * I}).data;
+    const float* f2 = wf.get(p + "mlp.fc2.weight", {D, I}).data;
+    dof[l].ln1 = bb.add_copy(wf.get(p + "input_layernorm.weight", {D}).data, D);
+    dof[l].ln2 = bb.add_copy(wf.get(p + "post_attention_layernorm.weight", {D}).data, D);
+    dof[l].ln3 = bb.add_copy(wf.get(p + "final_layernorm.weight", {D}).data, D);
+    dof[l].b2 = bb.add_copy(wf.get(p + "mlp.fc2.bias", {D}).data, D);
+    // per-head k-major blocks
+    dof[l].wqkv = bb.add((size_t)H * D * 3 * hd);
+    dof[l].wo = bb.add((size_t)H * hd * D);
+    dof[l].wqc = bb.add((size_t)H * D * hd);
+    dof[l].woc = bb.add((size_t)H * hd * D);
+    for (int h = 0; h < H; h++) {
+      float* wqkv = &bb.data[dof[l].wqkv + (size_t)h * D * 3 * hd];
+      float* wqc = &bb.data[dof[l].wqc + (size_t)h * D * hd];
+      for (int kk = 0; kk < D; kk++)
+        for (int n = 0; n < hd; n++) {
+          const size_t src = (size_t)(h * hd + n) * D + kk;
+          wqkv[(size_t)kk * 3 * hd + n] = q[src];
+          wqkv[(size_t)kk * 3 * hd + hd + n] = k[src];
+          wqkv[(size_t)kk * 3 * hd + 2 * hd + n] = v[src];
+          wqc[(size_t)kk * hd + n] = qc[src];
+        }
+      float* wo = &bb.data[dof[l].wo + (size_t)h * hd * D];
+      float* woc = &bb.data[dof[l].woc + (size_t)h * hd * D];
+      for (int kk = 0; kk < hd; kk++)
+        for (int n = 0; n < D; n++) {
+          wo[(size_t)kk * D + n] = o[(size_t)n * D + h * hd + kk];
+          woc[(size_t)kk * D + n] = oc[(size_t)n * D + h * hd + kk];
+        }
+    }
+    // MLP chunks: fc1 rows [0, I) are the value ("up"), [I, 2I) the gate
+    dof[l].w1 = bb.add((size_t)n_chunk * D * 2 * IC);
+    dof[l].b1 = bb.add((size_t)n_chunk * 2 * IC);
+    dof[l].w2 = bb.add((size_t)n_chunk * IC * D);
+    for (int c = 0; c < n_chunk; c++) {
+      float* w1 = &bb.data[dof[l].w1 + (size_t)c * D * 2 * IC];
+      float* b1 = &bb.data[dof[l].b1 + (size_t)c * 2 * IC];
+      float* w2 = &bb.data[dof[l].w2 + (size_t)c * IC * D];
+      for (int n = 0; n < IC; n++) {
+        b1[n] = f1b[c * IC + n];
+        b1[IC + n] = f1b[I + c * IC + n];
+        for (int kk = 0; kk < D; kk++) {
+          w1[(size_t)kk * 2 * IC + n] = f1[(size_t)(c * IC + n) * D + kk];
+          w1[(size_t)kk * 2 * IC + IC + n] = f1[(size_t)(I + c * IC + n) * D + kk];
+        }
+      }
+      for (int kk = 0; kk < IC; kk++)
+        for (int n = 0; n < D; n++) w2[(size_t)kk * D + n] = f2[(size_t)n * I + c * IC + kk];
+    }
+    std::memcpy(&bb.data[o_wk_all + (size_t)l * D * D], kc, sizeof(float) * D * D);
+    std::memcpy(&bb.data[o_wv_all + (size_t)l * D * D], vc, sizeof(float) * D * D);
+  }
+
+  wblob_.reserve(bb.data.size());
+  CUDA_CHECK(cudaMemcpyAsync(wblob_.ptr, bb.data.data(), bb.data.size() * sizeof(float),
+                             cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  const float* base = wblob_.ptr;
+  w1t_ = base + o_w1t; gn_w_ = base + o_gnw; gn_b_ = base + o_gnb;
+  conv2_w_ = base + o_c2; conv2_b_ = base + o_c2b; conv3_w_ = base + o_c3; conv3_b_ = base + o_c3b;
+  enc_.resize(d_.enc_layers);
+  for (int l = 0; l < d_.enc_layers; l++) {
+    enc_[l] = {base + eo[l].ln1, base + eo[l].wqk, base + eo[l].wv, base + eo[l].wo, base + eo[l].ln2,
+               base + eo[l].w1, base + eo[l].b1, base + eo[l].w2, base + eo[l].b2};
+  }
+  enc_final_ln_ = base + o_encln;
+  wk_all_ = base + o_wk_all;
+  wv_all_ = base + o_wv_all;
+  std::memset(&dec_, 0, sizeof(dec_));
+  dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
+  dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
+  dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
+  for (int l = 0; l < d_.dec_layers; l++) {
+    DecLayerWeights& w = dec_.layers[l];
+    w.ln1 = base + dof[l].ln1; w.wqkv = base + dof[l].wqkv; w.wo = base + dof[l].wo;
+    w.ln2 = base + dof[l].ln2; w.wqc = base + dof[l].wqc; w.woc = base + dof[l].woc;
+    w.ln3 = base + dof[l].ln3; w.w1 = base + dof[l].w1; w.b1 = base + dof[l].b1;
+    w.w2 = base + dof[l].w2; w.b2 = base + dof[l].b2;
+  }
+}
+
+void Model::ensure_rope(int max_pos) {
+  if (max_pos <= rope_positions_) return;
+  const int n = round_up(std::max(max_pos, 1024), 256);
+  const int half = d_.rot_dim / 2;
+  std::vector<float> c((size_t)n * half), s((size_t)n * half);
+  for (int j = 0; j < half; j++) {
+    // HF: inv_freq = 1 / theta ** (arange(0, dim, 2) / dim), dim = int(hd * factor)
+    const float inv_freq = (float)(1.0 / std::pow((double)d_.rope_theta, (2.0 * j) / (double)d_.rope_den));
+    for (int pos = 0; pos < n; pos++) {
+      const float ang = (float)pos * inv_freq;  // fp32 product like HF
+      c[(size_t)pos * half + j] = (float)std::cos((double)ang);
+      s[(size_t)pos * half + j] = (float)std::sin((double)ang);
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  rope_cos_.reserve(c.size());
+  rope_sin_.reserve(s.size());
+  CUDA_CHECK(cudaMemcpy(rope_cos_.ptr, c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(rope_sin_.ptr, s.data(), s.size() * sizeof(float), cudaMemcpyHostToDevice));
+  rope_positions_ = n;
+}
+
+void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B, float max_tps,
+                       std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  tokens.clear();
+  if (B <= 0) return;
+  uint64_t max_n = 0;
+  for (int b = 0; b < B; b++) max_n = std::max(max_n, n_samples[b]);
+  const int64_t stride = (int64_t)((max_n + 3) / 4 * 4);
+  pin_pcm_.reserve((size_t)B * stride);
+  pcm_dev_.reserve((size_t)B * stride);
+  for (int b = 0; b < B; b++) {
+    if (pcm[b] == nullptr && n_samples[b] > 0) throw std::runtime_error("Audio data is nullptr");
+    std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr, pin_pcm_.ptr, (size_t)B * stride * sizeof(float),
+                             cudaMemcpyHostToDevice, stream_));
+  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg);
+}
+
+void Model::transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
+                              float max_tps, std::vector<std::vector<int32_t>>& tokens,
+                              DebugCapture* dbg) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  tokens.clear();
+  if (B <= 0) return;
+  run(d_pcm, stride, n_samples, B, max_tps, tokens, dbg);
+}
+
+void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
+                std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg) {
+  const int D = d_.dim, I = d_.ffn, H = d_.heads, hd = d_.head_dim, V = d_.vocab;
+  const int L = d_.dec_layers;
+  times_ = StageTimes();
+  int launches = 0;
+  // MOONSHINE_B200_DEBUG_SYNC=<bitmask>: synchronise + check after stages
+  // (1 setup, 2 frontend, 4 encoder layers, 8 cross K/V, 16 decoder steps, 32 finalize).
+  static const int debug_sync = std::getenv("MOONSHINE_B200_DEBUG_SYNC") ? std::atoi(std::getenv("MOONSHINE_B200_DEBUG_SYNC")) : 0;
+  auto stage = [&](const char* name, int idx = -1, int bit = 0) {
+    if (!(debug_sync & bit)) return;
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      throw std::runtime_error(format("CUDA error %s after stage %s[%d] (B=%d): %s", cudaGetErrorName(e),
+                                      name, idx, B, cudaGetErrorString(e)));
+    }
+  };
+
+  // ---------------- plan ----------------
+  std::vector<int> T1(B), T2(B), T3(B), mlen(B), nsamp(B);
+  std::vector<int64_t> off1(B);
+  int64_t tot1 = 0;
+  int maxT1 = 0, maxT3 = 0, max_steps = 0;
+  for (int b = 0; b < B; b++) {
+    if (n_samples[b] == 0) throw std::runtime_error("Audio data is nullptr or empty");
+    if (n_samples[b] > (uint64_t)INT32_MAX) throw std::runtime_error("Audio segment too long");
+    frontend_lengths((int64_t)n_samples[b], T1[b], T2[b], T3[b]);
+    if (T3[b] < 1) {
+      throw std::runtime_error(format("Audio segment of %llu samples is too short for the encoder",
+                                      (unsigned long long)n_samples[b]));
+    }
+    nsamp[b] = (int)n_samples[b];
+    off1[b] = tot1;
+    tot1 += round_up(T1[b], 6);
+    maxT1 = std::max(maxT1, T1[b]);
+    maxT3 = std::max(maxT3, T3[b]);
+    mlen[b] = max_len_for(n_samples[b], max_tps);
+    max_steps = std::max(max_steps, mlen[b]);
+  }
+  const int64_t tot2 = tot1 / 3, tot3 = tot1 / 6;
+  const int Tp = round_up(maxT3, 4);      // encoder score / V^T row stride
+  const int Tpad = round_up(maxT3, 8);    // decoder cross K/V time padding
+  const int Smax = round_up(std::max(max_steps, 1) + 1, 4);
+  const int BH = B * H;
+  ensure_rope(std::max(maxT3, Smax) + 1);
+
+  // ---------------- metadata upload ----------------
+  // int32: nsamp[B] T1[B] T3[B] mlen[B] pos[tot3] MzT[BH] DzB[B]
+  // int64: off1[B] offQ[BH] offK[BH] offS[BH] offVh[BH] offO[BH] offXb[B] offVt[B] offKc[B] offVc[B]
+  const size_t n_i32 = (size_t)4 * B + tot3 + BH + B;
+  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B;
+  pin_i32_.reserve(n_i32);
+  pin_i64_.reserve(n_i64);
+  meta_i32_.reserve(n_i32);
+  meta_i64_.reserve(n_i64);
+  CUDA_CHECK(cudaStreamSynchronize(stream_));  // previous call may still read pinned staging
+  int* pi = pin_i32_.ptr;
+  int64_t* pl = pin_i64_.ptr;
+  int *h_ns = pi, *h_t1 = pi + B, *h_t3 = pi + 2 * B, *h_ml = pi + 3 * B, *h_pos = pi + 4 * B;
+  int* h_mzt = h_pos + tot3;
+  int* h_dzb = h_mzt + BH;
+  int64_t *h_off1 = pl, *h_offq = pl + B, *h_offk = h_offq + BH, *h_offs = h_offk + BH,
+          *h_offvh = h_offs + BH, *h_offo = h_offvh + BH, *h_offxb = h_offo + BH,
+          *h_offvt = h_offxb + B, *h_offkc = h_offvt + B, *h_offvc = h_offkc + B;
+  std::memset(h_pos, 0, sizeof(int) * tot3);
+  for (int b = 0; b < B; b++) {
+    h_ns[b] = nsamp[b]; h_t1[b] = T1[b]; h_t3[b] = T3[b]; h_ml[b] = mlen[b];
+    h_off1[b] = off1[b];
+    const int64_t r3 = off1[b] / 6;
+    for (int t = 0; t < T3[b]; t++) h_pos[r3 + t] = t;
+    h_dzb[b] = D;
+    h_offxb[b] = r3 * D;
+    h_offvt[b] = (int64_t)b * D * Tp;
+    h_offkc[b] = (int64_t)b * H * hd * Tpad;
+    h_offvc[b] = (int64_t)b * H * Tpad * hd;
+    for (int h = 0; h < H; h++) {
+      const int z = b * H + h;
+      h_mzt[z] = T3[b];
+      h_offq[z] = r3 * 2 * D + (int64_t)h * hd;
+      h_offk[z] = r3 * 2 * D + D + (int64_t)h * hd;
+      h_offs[z] = (int64_t)z * maxT3 * Tp;
+      h_offvh[z] = (int64_t)b * D * Tp + (int64_t)h * hd * Tp;
+      h_offo[z] = r3 * D + (int64_t)h * hd;
+    }
+  }
+  CUDA_CHECK(cudaMemcpyAsync(meta_i32_.ptr, pi, n_i32 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(meta_i64_.ptr, pl, n_i64 * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+  const int* d_ns = meta_i32_.ptr;
+  const int *d_t1 = d_ns + B, *d_t3 = d_ns + 2 * B, *d_ml = d_ns + 3 * B, *d_pos = d_ns + 4 * B;
+  const int* d_mzt = d_pos + tot3;
+  const int64_t* d_off1 = meta_i64_.ptr;
+  const int64_t *d_offq = d_off1 + B, *d_offk = d_offq + BH, *d_offs = d_offk + BH,
+                *d_offvh = d_offs + BH, *d_offo = d_offvh + BH, *d_offxb = d_offo + BH,
+                *d_offvt = d_offxb + B, *d_offkc = d_offvt + B, *d_offvc = d_offkc + B;
+
+  // ---------------- workspaces ----------------
+  auto reserve_zero = [&](DeviceBuffer<float>& buf, size_t n) {
+    if (n > buf.count) {
+      buf.reserve(n);
+      CUDA_CHECK(cudaMemsetAsync(buf.ptr, 0, buf.bytes(), stream_));
+    }
+  };
+  reserve_zero(h1_, (size_t)(tot1 + 8) * D);
+  reserve_zero(h2_, (size_t)(tot2 + 4) * 2 * D);
+  reserve_zero(x_, (size_t)tot3 * D);
+  reserve_zero(ln_, (size_t)tot3 * D);
+  reserve_zero(qk_, (size_t)tot3 * 2 * D);
+  reserve_zero(vt_, (size_t)B * D * Tp);
+  reserve_zero(scores_, (size_t)BH * maxT3 * Tp);
+  reserve_zero(attn_, (size_t)tot3 * D);
+  reserve_zero(mid_, (size_t)tot3 * I);
+  reserve_zero(enc_out_, (size_t)tot3 * D);
+  const int nblk = conv1_blocks_per_utt(maxT1);
+  gn_partial_.reserve((size_t)B * nblk * 2);
+  // V^T padding columns must stay finite: re-zero when the layout changes
+  CUDA_CHECK(cudaMemsetAsync(vt_.ptr, 0, (size_t)B * D * Tp * sizeof(float), stream_));
+
+  stage("setup", -1, 1);
+  if (timing_) CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+  // ---------------- frontend ----------------
+  launch_conv1_tanh(d_pcm, stride, d_ns, d_t1, d_off1, w1t_, h1_.ptr, D, B, maxT1, gn_partial_.ptr,
+                    nullptr, stream_);
+  stage("conv1", -1, 2);
+  launch_groupnorm_apply(h1_.ptr, d_t1, d_off1, gn_partial_.ptr, nblk, gn_w_, gn_b_, D, B, maxT1, stream_);
+  stage("groupnorm", -1, 2);
+  launches += 2;
+  {
+    // conv2 as a GEMM over overlapping row windows of the channel-last h1:
+    // output row r reads h1 rows 3r .. 3r+6 (7*D contiguous floats).
+    GemmParams g;
+    g.A = h1_.ptr; g.lda = 3 * D; g.W = conv2_w_; g.ldw = 7 * D; g.C = h2_.ptr; g.rs = 2 * D;
+    g.M = (int)tot2; g.N = 2 * D; g.K = 7 * D; g.bias = conv2_b_; g.act = 1;
+    launch_gemm(g, stream_);
+    GemmParams g3;
+    g3.A = h2_.ptr; g3.lda = 2 * 2 * D; g3.W = conv3_w_; g3.ldw = 3 * 2 * D; g3.C = x_.ptr; g3.rs = D;
+    g3.M = (int)tot3; g3.N = D; g3.K = 3 * 2 * D; g3.bias = conv3_b_; g3.act = 1;
+    stage("conv2", -1, 2);
+    launch_gemm(g3, stream_);
+    stage("conv3", -1, 2);
+    launches += 2;
+  }
+  if (timing_) CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+
+  // ---------------- encoder layers ----------------
+  const float scale = 1.0f / std::sqrt((float)hd);
+  for (int l = 0; l < d_.enc_layers; l++) {
+    const EncLayer& w = enc_[l];
+    launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, D, stream_);
+    {  // Q|K projection with fused interleaved RoPE
+      GemmParams g;
+      g.A = ln_.ptr; g.lda = D; g.W = w.wqk; g.ldw = D; g.C = qk_.ptr; g.rs = 2 * D;
+      g.M = (int)tot3; g.N = 2 * D; g.K = D;
+      g.pos = d_pos; g.rope_cos = rope_cos_.ptr; g.rope_sin = rope_sin_.ptr;
+      g.rope_cols = 2 * D; g.head_dim = hd; g.rot_dim = d_.rot_dim;
+      launch_gemm(g, stream_);
+    }
+    {  // V^T_b[D, T_b] = Wv * ln_b^T  (swapped orientation, per utterance)
+      GemmParams g;
+      g.A = w.wv; g.lda = D; g.strideA = 0; g.W = ln_.ptr; g.ldw = D; g.offW = d_offxb;
+      g.C = vt_.ptr; g.offC = d_offvt; g.rs = Tp;
+      g.groups = B; g.M = D; g.N = maxT3; g.K = D; g.Nz = d_t3;
+      launch_gemm(g, stream_);
+    }
+    {  // S_z = scale * Q_z K_z^T
+      GemmParams g;
+      g.A = qk_.ptr; g.lda = 2 * D; g.offA = d_offq; g.W = qk_.ptr; g.ldw = 2 * D; g.offW = d_offk;
+      g.C = scores_.ptr; g.offC = d_offs; g.rs = Tp;
+      g.groups = BH; g.M = maxT3; g.N = maxT3; g.K = hd; g.Mz = d_mzt; g.Nz = d_mzt;
+      g.alpha = scale;
+      launch_gemm(g, stream_);
+    }
+    launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_);
+    {  // O_z = P_z V_z
+      GemmParams g;
+      g.A = scores_.ptr; g.lda = Tp; g.offA = d_offs; g.W = vt_.ptr; g.ldw = Tp; g.offW = d_offvh;
+      g.C = attn_.ptr; g.offC = d_offo; g.rs = D;
+      g.groups = BH; g.M = maxT3; g.N = hd; g.K = maxT3; g.Mz = d_mzt; g.Kz = d_mzt;
+      launch_gemm(g, stream_);
+    }
+    {  // x += attn Wo^T
+      GemmParams g;
+      g.A = attn_.ptr; g.lda = D; g.W = w.wo; g.ldw = D; g.C = x_.ptr; g.rs = D;
+      g.M = (int)tot3; g.N = D; g.K = D; g.accumulate = 1;
+      launch_gemm(g, stream_);
+    }
+    launch_layernorm(x_.ptr, ln_.ptr, w.ln2, tot3, D, stream_);
+    {
+      GemmParams g;
+      g.A = ln_.ptr; g.lda = D; g.W = w.w1; g.ldw = D; g.C = mid_.ptr; g.rs = I;
+      g.M = (int)tot3; g.N = I; g.K = D; g.bias = w.b1; g.act = 1;
+      launch_gemm(g, stream_);
+      GemmParams g2;
+      g2.A = mid_.ptr; g2.lda = I; g2.W = w.w2; g2.ldw = I; g2.C = x_.ptr; g2.rs = D;
+      g2.M = (int)tot3; g2.N = D; g2.K = I; g2.bias = w.b2; g2.accumulate = 1;
+      launch_gemm(g2, stream_);
+    }
+    launches += 10;
+    stage("encoder_layer", l, 4);
+  }
+  launch_layernorm(x_.ptr, enc_out_.ptr, enc_final_ln_, tot3, D, stream_);
+  launches += 1;
+  if (timing_) CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+
+  if (dbg && dbg->encoder_out) {
+    dbg->encoder_out->clear();
+    if (dbg->encoder_frames) dbg->encoder_frames->assign(T3.begin(), T3.end());
+    std::vector<float> all((size_t)tot3 * D);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), enc_out_.ptr, all.size() * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (int b = 0; b < B; b++) {
+      const float* src = all.data() + (size_t)(off1[b] / 6) * D;
+      dbg->encoder_out->insert(dbg->encoder_out->end(), src, src + (size_t)T3[b] * D);
+    }
+  }
+  if (dbg && dbg->skip_decode) {
+    tokens.assign(B, std::vector<int32_t>());
+    return;
+  }
+
+  // ---------------- cross K/V (fp16, layouts of the step kernel) ----------------
+  const size_t kv_elems = (size_t)L * B * H * hd * Tpad;
+  if (kv_elems > kc_.count) {
+    kc_.reserve(kv_elems);
+    vc_.reserve(kv_elems);
+  }
+  CUDA_CHECK(cudaMemsetAsync(kc_.ptr, 0, kv_elems * sizeof(__half), stream_));
+  {
+    GemmParams g;  // K^T: rows (l, h, d), cols t
+    g.A = wk_all_; g.lda = D; g.W = enc_out_.ptr; g.ldw = D; g.offW = d_offxb;
+    g.C = kc_.ptr; g.offC = d_offkc; g.out_half = 1;
+    g.groups = B; g.M = L * D; g.N = maxT3; g.K = D; g.Nz = d_t3;
+    g.rm1 = D; g.rs1 = (int64_t)B * H * hd * Tpad; g.rm2 = hd; g.rs2 = (int64_t)hd * Tpad; g.rs = Tpad;
+    launch_gemm(g, stream_);
+    GemmParams v;  // V: rows t, cols (l, h, d)
+    v.A = enc_out_.ptr; v.lda = D; v.offA = d_offxb; v.W = wv_all_; v.ldw = D;
+    v.C = vc_.ptr; v.offC = d_offvc; v.out_half = 1;
+    v.groups = B; v.M = maxT3; v.N = L * D; v.K = D; v.Mz = d_t3;
+    v.rs = hd; v.cm1 = D; v.cs1 = (int64_t)B * H * Tpad * hd; v.cm2 = hd; v.cs2 = (int64_t)Tpad * hd;
+    launch_gemm(v, stream_);
+    launches += 2;
+    stage("cross_kv", -1, 8);
+  }
+  if (timing_) CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+
+  // ---------------- greedy decode ----------------
+  DecoderParams p = dec_;
+  p.B = B; p.Tpad = Tpad; p.Smax = Smax;
+  p.n_vchunk = 0;
+  {
+    int per = (V + sm_count_ - 1) / sm_count_;
+    per = round_up(std::max(per, 32), 32);
+    if (per > 256) per = 256;
+    p.vchunk = per;
+    p.n_vchunk = (V + per - 1) / per;
+  }
+  const size_t self_elems = (size_t)L * B * H * hd * Smax;
+  ks_.reserve(self_elems);
+  vs_.reserve(self_elems);
+  hbuf_.reserve((size_t)2 * B * D);
+  part_.reserve((size_t)(2 * H + p.n_chunk) * B * D);
+  xfin_.reserve((size_t)B * D);
+  cand_val_.reserve((size_t)2 * p.n_vchunk * B);
+  cand_idx_.reserve((size_t)2 * p.n_vchunk * B);
+  tokens_dev_.reserve((size_t)B * (Smax + 1));
+  ntok_dev_.reserve(B);
+  done_dev_.reserve(B);
+  pin_tokens_.reserve((size_t)B * (Smax + 1) + B + 1);
+  {
+    int* ht = pin_tokens_.ptr;
+    int* hn = ht + (size_t)B * (Smax + 1);
+    int* hact = hn + B;
+    int active = 0;
+    for (int b = 0; b < B; b++) {
+      for (int t = 0; t <= Smax; t++) ht[(size_t)b * (Smax + 1) + t] = 0;
+      ht[(size_t)b * (Smax + 1)] = d_.bos;
+      hn[b] = 1;
+      if (mlen[b] > 0) active++;
+    }
+    *hact = active;
+    CUDA_CHECK(cudaMemcpyAsync(tokens_dev_.ptr, ht, (size_t)B * (Smax + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(ntok_dev_.ptr, hn, B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(nactive_.ptr, hact, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemsetAsync(done_dev_.ptr, 0, B * sizeof(int), stream_));
+  }
+  p.rope_cos = rope_cos_.ptr; p.rope_sin = rope_sin_.ptr;
+  p.enc_len = d_t3; p.max_len = d_ml;
+  p.kc = kc_.ptr; p.vc = vc_.ptr; p.ks = ks_.ptr; p.vs = vs_.ptr;
+  p.hbuf = hbuf_.ptr; p.part = part_.ptr; p.xfin = xfin_.ptr;
+  p.cand_val = cand_val_.ptr; p.cand_idx = cand_idx_.ptr;
+  p.tokens = tokens_dev_.ptr; p.n_tokens = ntok_dev_.ptr; p.done = done_dev_.ptr;
+  p.n_active = nactive_.ptr; p.barrier = barrier_.ptr;
+  p.logits_out = nullptr; p.forced = nullptr;
+  int dbg_steps = 0;
+  if (dbg && dbg->forced) {
+    std::vector<int> f((size_t)B * (Smax + 1), 0);
+    for (int b = 0; b < B; b++)
+      for (int t = 0; t <= Smax && t < dbg->forced_stride; t++)
+        f[(size_t)b * (Smax + 1) + t] = dbg->forced[(size_t)b * dbg->forced_stride + t];
+    forced_dev_.reserve(f.size());
+    CUDA_CHECK(cudaMemcpy(forced_dev_.ptr, f.data(), f.size() * sizeof(int), cudaMemcpyHostToDevice));
+    p.forced = forced_dev_.ptr;
+  }
+  if (dbg && dbg->logits && dbg->logits_steps > 0) {
+    dbg_steps = std::min(dbg->logits_steps, max_steps);
+    logits_dbg_.reserve((size_t)dbg_steps * B * V);
+    CUDA_CHECK(cudaMemsetAsync(logits_dbg_.ptr, 0, (size_t)dbg_steps * B * V * sizeof(float), stream_));
+  }
+  const int grid = sm_count_;
+  for (int t = 0; t < max_steps; t++) {
+    p.step = t;
+    p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
+    launch_decoder_step(p, grid, stream_);
+    stage("decoder_step", t, 16);
+  }
+  p.step = max_steps;
+  launch_decoder_finalize(p, stream_);
+  stage("decoder_finalize", -1, 32);
+  times_.decode_steps = max_steps;
+  times_.decode_launches = max_steps + 1;
+  launches += max_steps + 1;
+  if (timing_) CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+
+  // ---------------- results ----------------
+  int* ht = pin_tokens_.ptr;
+  int* hn = ht + (size_t)B * (Smax + 1);
+  CUDA_CHECK(cudaMemcpyAsync(ht, tokens_dev_.ptr, (size_t)B * (Smax + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(hn, ntok_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  tokens.assign(B, std::vector<int32_t>());
+  for (int b = 0; b < B; b++) {
+    const int n = std::min(hn[b], Smax + 1);
+    tokens[b].assign(ht + (size_t)b * (Smax + 1), ht + (size_t)b * (Smax + 1) + n);
+  }
+  if (dbg && dbg->logits && dbg_steps > 0) {
+    dbg->logits->resize((size_t)dbg_steps * B * V);
+    CUDA_CHECK(cudaMemcpy(dbg->logits->data(), logits_dbg_.ptr, dbg->logits->size() * sizeof(float), cudaMemcpyDeviceToHost));
+    dbg->logits_steps = dbg_steps;
+  }
+  times_.kernel_launches = launches;
+  if (timing_) {
+    cudaEventElapsedTime(&times_.frontend_ms, ev_[0], ev_[1]);
+    cudaEventElapsedTime(&times_.encoder_ms, ev_[1], ev_[2]);
+    cudaEventElapsedTime(&times_.cross_kv_ms, ev_[2], ev_[3]);
+    cudaEventElapsedTime(&times_.decode_ms, ev_[3], ev_[4]);
+  }
+}
+
+}  // namespace msb

@@ -1,0 +1,108 @@
+// Device-side Moonshine model: weights in HBM + batched encoder / greedy
+// decoder.  This is the B200 replacement of the reference's MoonshineModel
+// (core/moonshine-model.{h,cpp}): same contract per utterance (PCM in ->
+// token ids out, start token 1, EOS 2 appended, at most
+// ceil(seconds * max_tokens_per_second) generated ids), but for a ragged
+// batch of utterances at once.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "weights.h"
+
+namespace msb {
+
+struct DebugCapture {
+  // Filled when non-null / true.
+  std::vector<float>* encoder_out = nullptr;     // packed [sum T_b][D]
+  std::vector<int>* encoder_frames = nullptr;    // T_b
+  std::vector<float>* logits = nullptr;          // [steps][B][V]
+  int logits_steps = 0;                          // capture the first N steps
+  const int32_t* forced = nullptr;               // [B][forced_stride] teacher-forced ids (incl. start)
+  int forced_stride = 0;
+  bool skip_decode = false;
+};
+
+struct StageTimes {
+  float frontend_ms = 0, encoder_ms = 0, cross_kv_ms = 0, decode_ms = 0;
+  int decode_steps = 0;
+  int decode_launches = 0;
+  int kernel_launches = 0;
+};
+
+class Model {
+ public:
+  Model(const Dims& dims, const WeightFile& weights, int device);
+  ~Model();
+
+  const Dims& dims() const { return d_; }
+  int device() const { return device_; }
+  cudaStream_t stream() const { return stream_; }
+
+  // Host PCM (16 kHz mono float).  Copies to the device inside the call.
+  void transcribe(const float* const* pcm, const uint64_t* n_samples, int B,
+                  float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
+                  DebugCapture* dbg = nullptr);
+  // Device-resident PCM: row b at d_pcm + b * stride.
+  void transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
+                         float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
+                         DebugCapture* dbg = nullptr);
+
+  // reference rule: core/moonshine-model.cpp:347-349
+  static int max_len_for(uint64_t n_samples, float max_tokens_per_second);
+
+  const StageTimes& last_times() const { return times_; }
+  void set_timing(bool on) { timing_ = on; }
+  size_t weight_bytes() const { return wblob_.bytes(); }
+
+ private:
+  struct EncLayer {
+    const float *ln1, *wqk, *wv, *wo, *ln2, *w1, *b1, *w2, *b2;
+  };
+  void build_weights(const WeightFile& wf);
+  void ensure_rope(int max_pos);
+  void run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
+           std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg);
+
+  Dims d_;
+  int device_ = 0;
+  int sm_count_ = 0;
+  cudaStream_t stream_ = nullptr;
+  bool timing_ = false;
+  StageTimes times_;
+  cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  // weights
+  DeviceBuffer<float> wblob_;
+  const float *w1t_ = nullptr, *gn_w_ = nullptr, *gn_b_ = nullptr;
+  const float *conv2_w_ = nullptr, *conv2_b_ = nullptr, *conv3_w_ = nullptr, *conv3_b_ = nullptr;
+  std::vector<EncLayer> enc_;
+  const float* enc_final_ln_ = nullptr;
+  const float *wk_all_ = nullptr, *wv_all_ = nullptr;
+  DecoderParams dec_{};  // weight pointers + dims prefilled
+  int ffn_chunk_ = 64;
+
+  // rope tables (grow-only)
+  DeviceBuffer<float> rope_cos_, rope_sin_;
+  int rope_positions_ = 0;
+
+  // workspaces (grow-only)
+  DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_;
+  DeviceBuffer<double> gn_partial_;
+  DeviceBuffer<__half> kc_, vc_;
+  DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_;
+  DeviceBuffer<int> cand_idx_, tokens_dev_, ntok_dev_, done_dev_, forced_dev_;
+  DeviceBuffer<int> meta_i32_;       // packed int32 metadata
+  DeviceBuffer<int64_t> meta_i64_;   // packed int64 metadata
+  DeviceBuffer<unsigned int> barrier_;
+  DeviceBuffer<int> nactive_;
+  PinnedBuffer<int> pin_i32_;
+  PinnedBuffer<int64_t> pin_i64_;
+  PinnedBuffer<float> pin_pcm_;
+  PinnedBuffer<int> pin_tokens_;
+};
+
+}  // namespace msb

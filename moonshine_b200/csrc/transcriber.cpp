@@ -1,0 +1,477 @@
+#include "transcriber.h"
+
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cmath>
+#include <numeric>
+#include <random>
+
+namespace msb {
+
+namespace {
+constexpr int kSampleRate = 16000;
+float seconds_from_samples(size_t n) { return static_cast<float>(n) / kSampleRate; }
+bool file_exists(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+bool dir_exists(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Resampler: behaviour of core/resampler.cpp:5-86 (box average down, linear
+// interpolation up, float arithmetic).
+// ---------------------------------------------------------------------------
+std::vector<float> resample_audio(const float* audio, size_t n, float in_rate, float out_rate) {
+  if (in_rate == out_rate) return std::vector<float>(audio, audio + n);
+  const size_t out_n = (size_t)(n * out_rate / in_rate);
+  std::vector<float> out(out_n);
+  const float ratio = in_rate / out_rate;
+  if (in_rate > out_rate) {
+    for (size_t i = 0; i < out_n; i++) {
+      size_t a = (size_t)(i * ratio);
+      size_t b = (size_t)((i + 1) * ratio);
+      if (b >= n) b = n - 1;
+      float sum = 0.f;
+      size_t cnt = 0;
+      for (size_t j = a; j <= b; j++) { sum += audio[j]; cnt++; }
+      out[i] = cnt > 0 ? sum / cnt : 0.f;
+    }
+  } else {
+    for (size_t i = 0; i < out_n; i++) {
+      const float pos = i * ratio;
+      const size_t idx = (size_t)pos;
+      const float frac = pos - idx;
+      if (idx >= n - 1) out[i] = audio[n - 1];
+      else out[i] = audio[idx] + frac * (audio[idx + 1] - audio[idx]);
+    }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// Segmenter
+// ---------------------------------------------------------------------------
+Segmenter::Segmenter(float threshold, int window_size, int hop_size, size_t look_behind,
+                     size_t max_segment)
+    : threshold_(threshold), window_size_(window_size < 1 ? 1 : window_size),
+      hop_size_(hop_size < 1 ? 512 : hop_size), look_behind_count_(look_behind),
+      max_segment_(max_segment) {
+  probability_window_.assign(window_size_, 0.f);
+  look_behind_.assign(look_behind_count_, 0.f);
+}
+
+void Segmenter::start() {
+  active_ = true;
+  samples_processed_ = 0;
+  segments_.clear();
+  current_.clear();
+  look_behind_.assign(look_behind_count_, 0.f);
+  remainder_.clear();
+  probability_window_.assign(window_size_, 0.f);
+  probability_index_ = 0;
+  previous_is_voice_ = false;
+}
+
+void Segmenter::stop() {
+  active_ = false;
+  if (previous_is_voice_) on_voice_end();
+}
+
+void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate) {
+  if (!active_) return;
+  for (Segment& s : segments_) s.just_updated = false;
+  std::vector<float> buf = remainder_;
+  if (sample_rate == kSampleRate) {
+    buf.insert(buf.end(), audio, audio + n);
+  } else {
+    std::vector<float> r = resample_audio(audio, n, (float)sample_rate, (float)kSampleRate);
+    buf.insert(buf.end(), r.begin(), r.end());
+  }
+  size_t pos = 0;
+  while (buf.size() - pos >= (size_t)hop_size_) {
+    process_hop(buf.data() + pos);
+    pos += hop_size_;
+  }
+  remainder_.assign(buf.begin() + pos, buf.end());
+}
+
+void Segmenter::process_hop(const float* hop) {
+  samples_processed_ += hop_size_;
+  if (look_behind_.size() >= (size_t)hop_size_) {
+    std::move(look_behind_.begin() + hop_size_, look_behind_.end(), look_behind_.begin());
+    std::copy(hop, hop + hop_size_, look_behind_.end() - hop_size_);
+  } else if (!look_behind_.empty()) {
+    std::copy(hop + hop_size_ - look_behind_.size(), hop + hop_size_, look_behind_.begin());
+  }
+  float smoothed;
+  if (threshold_ > 0.0f) {
+    probability_window_[probability_index_] = 1.0f;  // constant speech probability
+    probability_index_ = (probability_index_ + 1) % probability_window_.size();
+    smoothed = std::accumulate(probability_window_.begin(), probability_window_.end(), 0.0f) /
+               probability_window_.size();
+  } else {
+    smoothed = 1.0f;
+  }
+  const size_t fade = (max_segment_ * 2) / 3;
+  if (max_segment_ && current_.size() > fade) {
+    const float fade_factor = static_cast<float>(current_.size() - fade) / fade;
+    smoothed *= fade_factor;
+  }
+  const bool is_voice = smoothed > threshold_;
+  if (is_voice && !previous_is_voice_) {
+    const size_t lb = std::min(look_behind_.size(), samples_processed_);
+    current_.assign(look_behind_.end() - lb, look_behind_.end());
+    if (look_behind_.size() < (size_t)hop_size_ && lb < (size_t)hop_size_) {
+      // look-behind shorter than a hop: the hop itself still starts the segment
+      current_.assign(hop, hop + hop_size_);
+    }
+    on_voice_start();
+  } else if (!is_voice && previous_is_voice_) {
+    current_.insert(current_.end(), hop, hop + hop_size_);
+    on_voice_end();
+    current_.clear();
+    look_behind_.assign(look_behind_count_, 0.f);
+  } else if (is_voice && previous_is_voice_) {
+    current_.insert(current_.end(), hop, hop + hop_size_);
+    on_voice_continuing();
+  }
+  previous_is_voice_ = is_voice;
+}
+
+void Segmenter::on_voice_start() {
+  segments_.emplace_back();
+  Segment& s = segments_.back();
+  const float now = seconds_from_samples(samples_processed_);
+  s.audio = current_;
+  s.start_time = now - seconds_from_samples(current_.size());
+  s.end_time = now;
+  s.is_complete = false;
+  s.just_updated = true;
+}
+void Segmenter::on_voice_continuing() {
+  Segment& s = segments_.back();
+  s.audio = current_;
+  s.end_time = seconds_from_samples(samples_processed_);
+  s.is_complete = false;
+  s.just_updated = true;
+}
+void Segmenter::on_voice_end() {
+  Segment& s = segments_.back();
+  s.audio = current_;
+  s.end_time = seconds_from_samples(samples_processed_);
+  s.is_complete = true;
+  s.just_updated = true;
+}
+
+// ---------------------------------------------------------------------------
+// TranscriptOutput (reference: TranscriptStreamOutput, transcriber.cpp:1627-1760)
+// ---------------------------------------------------------------------------
+void TranscriptOutput::clear() {
+  lines.clear();
+  order.clear();
+  c_lines_.clear();
+  transcript.lines = nullptr;
+  transcript.line_count = 0;
+}
+void TranscriptOutput::clear_update_flags() {
+  for (uint64_t id : order) {
+    Line& l = lines[id];
+    l.just_updated = 0;
+    l.is_new = 0;
+    l.has_text_changed = 0;
+  }
+  rebuild();
+}
+void TranscriptOutput::add_or_update(Line& line) {
+  auto it = lines.find(line.id);
+  if (it != lines.end()) {
+    line.is_new = 0;
+    const Line& old = it->second;
+    line.has_text_changed = (old.has_text != line.has_text) ||
+                            (old.has_text && line.has_text && old.text != line.text);
+  } else {
+    line.is_new = 1;
+    line.has_text_changed = line.has_text ? 1 : 0;
+  }
+  lines[line.id] = line;
+}
+void TranscriptOutput::mark_all_complete() {
+  for (uint64_t id : order) {
+    Line& l = lines[id];
+    if (!l.is_complete) {
+      l.is_complete = 1;
+      l.just_updated = 1;
+    }
+  }
+  rebuild();
+}
+void TranscriptOutput::rebuild() {
+  c_lines_.clear();
+  c_lines_.reserve(order.size());
+  for (uint64_t id : order) {
+    const Line& l = lines[id];
+    transcript_line_t c{};
+    c.text = l.has_text ? l.text.c_str() : nullptr;
+    c.audio_data = l.audio.empty() ? nullptr : l.audio.data();
+    c.audio_data_count = l.audio.size();
+    c.start_time = l.start_time;
+    c.duration = l.duration;
+    c.id = l.id;
+    c.is_complete = l.is_complete;
+    c.is_updated = l.just_updated;
+    c.is_new = l.is_new;
+    c.has_text_changed = l.has_text_changed;
+    c.have_speakers_changed = 0;
+    c.speaker_spans = nullptr;
+    c.speaker_span_count = 0;
+    c.last_transcription_latency_ms = l.latency_ms;
+    c.words = nullptr;
+    c.word_count = 0;
+    c_lines_.push_back(c);
+  }
+  transcript.lines = c_lines_.empty() ? nullptr : c_lines_.data();
+  transcript.line_count = c_lines_.size();
+}
+
+// ---------------------------------------------------------------------------
+// Transcriber
+// ---------------------------------------------------------------------------
+Transcriber::Transcriber(const TranscriberOptions& options, uint32_t model_arch)
+    : options_(options), arch_(model_arch) {
+  std::random_device rd;
+  next_line_id_ = ((uint64_t)rd() << 32) | (uint64_t)rd();
+}
+
+Transcriber::~Transcriber() {}
+
+std::unique_ptr<Segmenter> Transcriber::make_segmenter() const {
+  const int window =
+      (int)std::ceil((options_.vad_window_duration * kSampleRate) / options_.vad_hop_size);
+  const size_t max_seg = (size_t)std::round(options_.vad_max_segment_duration * kSampleRate);
+  return std::make_unique<Segmenter>(options_.vad_threshold, window, options_.vad_hop_size,
+                                     options_.vad_look_behind_sample_count, max_seg);
+}
+
+static int pick_device(int requested) {
+  if (requested >= 0) return requested;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    throw std::runtime_error("No CUDA device available: moonshine-b200 has no CPU fallback");
+  }
+  return dev;
+}
+
+void Transcriber::load_from_directory(const std::string& path) {
+  if (options_.skip_transcription) return;
+  if (!dir_exists(path)) throw std::runtime_error("Model directory '" + path + "' does not exist");
+  const std::string wpath = path + "/model.msw";
+  const std::string tpath = path + "/tokenizer.bin";
+  if (!file_exists(wpath)) {
+    throw std::runtime_error(
+        "'" + wpath + "' not found. moonshine-b200 loads float weights from model.msw "
+        "(see moonshine_b200/weights.py); ONNX Runtime .ort graphs cannot be executed here.");
+  }
+  if (!file_exists(tpath)) throw std::runtime_error("Failed to open tokenizer file at " + tpath);
+  WeightFile wf;
+  load_msw_file(wpath, wf);
+  if (wf.arch != arch_) {
+    throw std::runtime_error(format("model.msw holds architecture %u but %u was requested. This "
+                                    "often indicates you're specifying the wrong model architecture",
+                                    wf.arch, arch_));
+  }
+  tokenizer_.reset(Tokenizer::from_file(tpath));
+  model_ = std::make_unique<Model>(dims_for_arch(arch_), wf, pick_device(options_.device));
+}
+
+void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
+                                   const uint8_t* tokenizer, size_t tokenizer_size) {
+  if (options_.skip_transcription) return;
+  WeightFile wf;
+  parse_msw(weights, weights_size, wf);
+  if (wf.arch != arch_) {
+    throw std::runtime_error(format("model.msw holds architecture %u but %u was requested", wf.arch, arch_));
+  }
+  tokenizer_ = std::make_unique<Tokenizer>(tokenizer, tokenizer_size);
+  model_ = std::make_unique<Model>(dims_for_arch(arch_), wf, pick_device(options_.device));
+}
+
+// One batched model call for every just_updated segment of every job.
+// Reference: Transcriber::update_transcript_from_segments
+// (core/transcriber.cpp:989-1148), which runs the segments serially.
+void Transcriber::update_outputs(std::vector<Job>& jobs) {
+  struct Pending { size_t job; size_t seg; Line line; bool run; };
+  std::vector<Pending> pend;
+  std::vector<const float*> ptrs;
+  std::vector<uint64_t> lens;
+  for (size_t j = 0; j < jobs.size(); j++) {
+    jobs[j].output->clear_update_flags();
+    std::vector<Segment>& segs = *jobs[j].segments;
+    for (size_t si = 0; si < segs.size(); si++) {
+      Segment& s = segs[si];
+      if (!s.just_updated) continue;
+      Pending p;
+      p.job = j; p.seg = si; p.run = false;
+      p.line.start_time = s.start_time;
+      p.line.duration = s.end_time - s.start_time;
+      p.line.is_complete = s.is_complete;
+      p.line.just_updated = s.just_updated;
+      TranscriptOutput& out = *jobs[j].output;
+      if (si >= out.order.size()) out.order.push_back(next_line_id_.fetch_add(1));
+      p.line.id = out.order.at(si);
+      if (model_) {
+        if (!s.is_complete && !options_.decode_incomplete_lines) {
+          p.line.has_text = true;  // empty string, like the reference
+        } else {
+          p.run = true;
+          ptrs.push_back(s.audio.data());
+          lens.push_back(s.audio.size());
+        }
+      }
+      pend.push_back(std::move(p));
+    }
+  }
+  std::vector<std::vector<int32_t>> tokens;
+  uint32_t latency_ms = 0;
+  if (!ptrs.empty()) {
+    std::lock_guard<std::mutex> lock(model_mutex_);
+    const auto t0 = std::chrono::steady_clock::now();
+    model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens);
+    latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
+                     std::chrono::steady_clock::now() - t0).count();
+  }
+  size_t ti = 0;
+  for (Pending& p : pend) {
+    Segment& s = (*jobs[p.job].segments)[p.seg];
+    if (p.run) {
+      const std::string text = tokenizer_->tokens_to_text(tokens[ti++]);
+      if (options_.log_output_text) MSB_LOGF("Transcribed text: '%s'", text.c_str());
+      p.line.text = sanitize_utf8(text);
+      p.line.has_text = true;
+      p.line.latency_ms = latency_ms;
+    }
+    if (options_.return_audio_data) p.line.audio = s.audio;
+    jobs[p.job].output->add_or_update(p.line);
+  }
+  for (Job& j : jobs) {
+    if (j.stopped) j.output->mark_all_complete();
+    j.output->rebuild();
+  }
+}
+
+void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* lengths,
+                                   uint64_t count, int32_t sample_rate, uint32_t flags,
+                                   transcript_t** out) {
+  (void)flags;
+  std::lock_guard<std::mutex> lock(batch_mutex_);
+  // every call starts from fresh line state, like stream->start() does for
+  // the reference's batch stream (transcriber.cpp:679-683)
+  batch_outputs_.clear();
+  batch_transcripts_.assign(count, transcript_t{nullptr, 0});
+  std::vector<std::unique_ptr<Segmenter>> vads;
+  std::vector<Job> jobs;
+  for (uint64_t i = 0; i < count; i++) {
+    if (audio[i] == nullptr && lengths[i] > 0) throw std::runtime_error("Audio data is nullptr");
+    batch_outputs_.push_back(std::make_unique<TranscriptOutput>());
+    vads.push_back(make_segmenter());
+    vads.back()->start();
+    vads.back()->process_audio(audio[i], (size_t)lengths[i], sample_rate);
+    vads.back()->stop();
+    jobs.push_back(Job{batch_outputs_.back().get(), &vads.back()->segments(), true});
+  }
+  update_outputs(jobs);
+  for (uint64_t i = 0; i < count; i++) batch_transcripts_[i] = batch_outputs_[i]->transcript;
+  if (out) *out = batch_transcripts_.data();
+}
+
+void Transcriber::transcribe_without_streaming(const float* audio, uint64_t n, int32_t sample_rate,
+                                               uint32_t flags, transcript_t** out) {
+  const float* ptrs[1] = {audio};
+  uint64_t lens[1] = {n};
+  transcribe_batch(ptrs, lens, 1, sample_rate, flags, out);
+}
+
+int32_t Transcriber::create_stream() {
+  std::lock_guard<std::mutex> lock(streams_mutex_);
+  const int32_t id = next_stream_id_++;
+  auto s = std::make_unique<Stream>();
+  s->vad = make_segmenter();
+  streams_[id] = std::move(s);
+  return id;
+}
+
+Stream* Transcriber::find_stream(int32_t id) {
+  std::lock_guard<std::mutex> lock(streams_mutex_);
+  auto it = streams_.find(id);
+  if (it == streams_.end()) {
+    throw std::runtime_error("Stream with ID " + std::to_string(id) + " not found in " +
+                             std::to_string(streams_.size()) + " streams");
+  }
+  return it->second.get();
+}
+
+void Transcriber::free_stream(int32_t id) {
+  std::lock_guard<std::mutex> lock(streams_mutex_);
+  if (streams_.erase(id) == 0) throw std::runtime_error("Stream with ID " + std::to_string(id) + " not found");
+}
+
+void Transcriber::start_stream(int32_t id) {
+  Stream* s = find_stream(id);
+  std::lock_guard<std::mutex> lock(s->mutex);
+  s->output.clear();
+  s->new_audio.clear();
+  s->vad->start();
+}
+
+void Transcriber::stop_stream(int32_t id) {
+  Stream* s = find_stream(id);
+  std::lock_guard<std::mutex> lock(s->mutex);
+  s->vad->stop();
+}
+
+void Transcriber::add_audio_to_stream(int32_t id, const float* audio, uint64_t n, int32_t sample_rate) {
+  Stream* s = find_stream(id);
+  std::lock_guard<std::mutex> lock(s->mutex);
+  if (!s->vad->is_active()) {
+    throw std::runtime_error("Adding new audio for stream with ID " + std::to_string(id) +
+                             " but VAD is not active. Did you call start_stream()?");
+  }
+  if (sample_rate == kSampleRate) {
+    s->new_audio.insert(s->new_audio.end(), audio, audio + n);
+  } else {
+    std::vector<float> r = resample_audio(audio, (size_t)n, (float)sample_rate, (float)kSampleRate);
+    s->new_audio.insert(s->new_audio.end(), r.begin(), r.end());
+  }
+}
+
+// Reference: Transcriber::transcribe_stream, core/transcriber.cpp:775-913.
+void Transcriber::transcribe_stream(int32_t id, uint32_t flags, transcript_t** out) {
+  Stream* s = find_stream(id);
+  std::lock_guard<std::mutex> lock(s->mutex);
+  const bool has_new = !s->new_audio.empty();
+  const float new_dur = s->new_audio.size() / (float)kSampleRate;
+  const bool should_update =
+      ((new_dur >= options_.transcription_interval) || (flags & MOONSHINE_FLAG_FORCE_UPDATE)) && has_new;
+  const bool stopped = !s->vad->is_active();
+  if (!should_update) {
+    s->output.clear_update_flags();
+    if (stopped) s->output.mark_all_complete();
+    if (out) *out = &s->output.transcript;
+    return;
+  }
+  s->vad->process_audio(s->new_audio.data(), s->new_audio.size(), kSampleRate);
+  s->new_audio.clear();
+  std::vector<Job> jobs{Job{&s->output, &s->vad->segments(), stopped}};
+  update_outputs(jobs);
+  if (!options_.return_audio_data) {
+    for (Segment& seg : s->vad->segments())
+      if (seg.is_complete) std::vector<float>().swap(seg.audio);
+  }
+  if (out) *out = &s->output.transcript;
+}
+
+}  // namespace msb

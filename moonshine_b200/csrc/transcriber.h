@@ -1,0 +1,163 @@
+// Host-side transcriber: segmentation, line bookkeeping, streams and the
+// transcript_t storage the C ABI hands out.  Mirrors the behaviour contract of
+// the reference's Transcriber (core/transcriber.{h,cpp}) for the TINY/BASE
+// architectures; the model behind it is the CUDA `Model`.
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/moonshine_b200.h"
+#include "model.h"
+#include "tokenizer.h"
+
+namespace msb {
+
+// Option names and defaults: core/transcriber.h:181-229,
+// parsing: core/moonshine-c-api.cpp:129-198.
+struct TranscriberOptions {
+  bool skip_transcription = false;
+  float transcription_interval = 0.5f;
+  float vad_threshold = 0.5f;
+  float vad_window_duration = 0.5f;
+  int32_t vad_hop_size = 512;
+  size_t vad_look_behind_sample_count = 8192;
+  float vad_max_segment_duration = 15.0f;
+  float max_tokens_per_second = 6.5f;
+  bool decode_incomplete_lines = true;
+  bool return_audio_data = true;
+  bool log_output_text = false;
+  bool word_timestamps = false;
+  bool identify_speakers = false;
+  std::vector<std::string> keyterms;
+  std::string context;
+  int device = -1;  // additive option "device": CUDA ordinal (-1 = current / LOCAL_RANK)
+};
+
+struct Segment {
+  std::vector<float> audio;
+  float start_time = 0.f;
+  float end_time = 0.f;
+  bool is_complete = false;
+  bool just_updated = false;
+};
+
+// The reference's VoiceActivityDetector (core/voice-activity-detector.cpp)
+// with the Silero model replaced by a constant speech probability of 1.0:
+// identical hop / look-behind / smoothing-window / max-segment-fade logic,
+// so `vad_threshold=0` (the documented bypass, :139,152-157) behaves exactly
+// like the reference.  The Silero network itself is out of scope.
+class Segmenter {
+ public:
+  Segmenter(float threshold, int window_size, int hop_size, size_t look_behind, size_t max_segment);
+  void start();
+  void stop();
+  bool is_active() const { return active_; }
+  void process_audio(const float* audio, size_t n, int32_t sample_rate);
+  std::vector<Segment>& segments() { return segments_; }
+
+ private:
+  void process_hop(const float* hop);
+  void on_voice_start();
+  void on_voice_continuing();
+  void on_voice_end();
+  float threshold_;
+  int window_size_, hop_size_;
+  size_t look_behind_count_, max_segment_;
+  bool active_ = false, previous_is_voice_ = false;
+  size_t samples_processed_ = 0;
+  std::vector<float> probability_window_;
+  size_t probability_index_ = 0;
+  std::vector<float> look_behind_, current_, remainder_;
+  std::vector<Segment> segments_;
+};
+
+struct Line {
+  bool has_text = false;
+  std::string text;
+  std::vector<float> audio;
+  float start_time = 0.f, duration = 0.f;
+  uint64_t id = 0;
+  int8_t is_complete = 0, just_updated = 0, is_new = 0, has_text_changed = 0;
+  uint32_t latency_ms = 0;
+};
+
+class TranscriptOutput {
+ public:
+  void clear();
+  void clear_update_flags();
+  void add_or_update(Line& line);
+  void mark_all_complete();
+  void rebuild();
+  transcript_t transcript{nullptr, 0};
+  std::map<uint64_t, Line> lines;
+  std::vector<uint64_t> order;
+
+ private:
+  std::vector<transcript_line_t> c_lines_;
+};
+
+struct Stream {
+  std::unique_ptr<Segmenter> vad;
+  TranscriptOutput output;
+  std::vector<float> new_audio;  // 16 kHz, not yet analysed
+  std::mutex mutex;
+};
+
+std::vector<float> resample_audio(const float* audio, size_t n, float in_rate, float out_rate);
+
+class Transcriber {
+ public:
+  Transcriber(const TranscriberOptions& options, uint32_t model_arch);
+  ~Transcriber();
+  void load_from_directory(const std::string& path);
+  void load_from_memory(const uint8_t* weights, size_t weights_size, const uint8_t* tokenizer,
+                        size_t tokenizer_size);
+
+  void transcribe_without_streaming(const float* audio, uint64_t n, int32_t sample_rate,
+                                    uint32_t flags, transcript_t** out);
+  void transcribe_batch(const float* const* audio, const uint64_t* lengths, uint64_t count,
+                        int32_t sample_rate, uint32_t flags, transcript_t** out);
+  int32_t create_stream();
+  void free_stream(int32_t id);
+  void start_stream(int32_t id);
+  void stop_stream(int32_t id);
+  void add_audio_to_stream(int32_t id, const float* audio, uint64_t n, int32_t sample_rate);
+  void transcribe_stream(int32_t id, uint32_t flags, transcript_t** out);
+
+  Model* model() { return model_.get(); }
+  std::mutex& model_mutex() { return model_mutex_; }
+  const TranscriberOptions& options() const { return options_; }
+  uint32_t arch() const { return arch_; }
+
+ private:
+  std::unique_ptr<Segmenter> make_segmenter() const;
+  Stream* find_stream(int32_t id);
+  // Transcribes every just_updated segment of every (stream, segments) pair in
+  // ONE batched model call and writes the lines.
+  struct Job {
+    TranscriptOutput* output;
+    std::vector<Segment>* segments;
+    bool stopped;
+  };
+  void update_outputs(std::vector<Job>& jobs);
+
+  TranscriberOptions options_;
+  uint32_t arch_;
+  std::unique_ptr<Model> model_;
+  std::unique_ptr<Tokenizer> tokenizer_;
+  std::mutex model_mutex_;      // serialises model use (reference: stt_model_mutex)
+  std::mutex batch_mutex_;      // reference: batch_stream_mutex
+  std::mutex streams_mutex_;
+  std::map<int32_t, std::unique_ptr<Stream>> streams_;
+  int32_t next_stream_id_ = 1;  // reference: stream ids start at 1 (transcriber.cpp:104)
+  std::atomic<uint64_t> next_line_id_;
+  // storage behind the non-streaming results
+  std::vector<std::unique_ptr<TranscriptOutput>> batch_outputs_;
+  std::vector<transcript_t> batch_transcripts_;
+};
+
+}  // namespace msb
