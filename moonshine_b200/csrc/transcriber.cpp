@@ -98,6 +98,16 @@ void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate)
     pos += hop_size_;
   }
   remainder_.assign(buf.begin() + pos, buf.end());
+  sync_open_segment_audio();
+}
+
+// The reference copies the growing segment buffer into the segment on every
+// hop (O(n^2) per clip); the observable state only matters when a call
+// returns, so the still-open segment is materialised once here.
+void Segmenter::sync_open_segment_audio() {
+  if (previous_is_voice_ && !segments_.empty() && !segments_.back().is_complete) {
+    segments_.back().audio = current_;
+  }
 }
 
 void Segmenter::process_hop(const float* hop) {
@@ -147,7 +157,6 @@ void Segmenter::on_voice_start() {
   segments_.emplace_back();
   Segment& s = segments_.back();
   const float now = seconds_from_samples(samples_processed_);
-  s.audio = current_;
   s.start_time = now - seconds_from_samples(current_.size());
   s.end_time = now;
   s.is_complete = false;
@@ -155,7 +164,6 @@ void Segmenter::on_voice_start() {
 }
 void Segmenter::on_voice_continuing() {
   Segment& s = segments_.back();
-  s.audio = current_;
   s.end_time = seconds_from_samples(samples_processed_);
   s.is_complete = false;
   s.just_updated = true;

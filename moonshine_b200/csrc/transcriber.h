@@ -61,6 +61,7 @@ class Segmenter {
 
  private:
   void process_hop(const float* hop);
+  void sync_open_segment_audio();
   void on_voice_start();
   void on_voice_continuing();
   void on_voice_end();
