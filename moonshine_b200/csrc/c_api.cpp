@@ -438,12 +438,13 @@ int32_t moonshine_b200_debug_run(int32_t transcriber_handle, const float* const*
 int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, int32_t M, int32_t N,
                                  int32_t K, int32_t lda, int32_t ldw, int32_t ldc, const float* d_bias,
                                  int32_t act, int32_t accumulate, int32_t impl) {
-  (void)impl;
   try {
     GemmParams g;
     g.A = dA; g.W = dW; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.rs = ldc;
     g.bias = d_bias; g.act = act; g.accumulate = accumulate;
-    launch_gemm(g, nullptr);
+    if (impl == 1) launch_gemm_simt(g, nullptr);
+    else if (impl == 2) launch_gemm_tc(g, nullptr);
+    else launch_gemm(g, nullptr);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaDeviceSynchronize());
   } catch (const std::exception& e) {

@@ -7,6 +7,7 @@
 // 8x8 register tile per thread, register-staged double buffering.
 #include <cuda_fp16.h>
 
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 
 namespace msb {
@@ -15,17 +16,6 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int PAD = 4;
-
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-
-__device__ __forceinline__ int64_t split_off(int i, int m1, int m2, int64_t s1, int64_t s2,
-                                             int64_t s3) {
-  if (m1 == 0) return (int64_t)i * s3;
-  int r = i % m1;
-  return (int64_t)(i / m1) * s1 + (int64_t)(r / m2) * s2 + (int64_t)(r % m2) * s3;
-}
 
 __global__ void __launch_bounds__(256, 2) gemm_nt_kernel(GemmParams p) {
   const int z = blockIdx.z;
@@ -121,84 +111,19 @@ __global__ void __launch_bounds__(256, 2) gemm_nt_kernel(GemmParams p) {
   }
 
   // ---- epilogue ----
-  const int half_rot = p.rot_dim >> 1;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= Mz) continue;
-    const int64_t roff = c_base + split_off(m, p.rm1, p.rm2, p.rs1, p.rs2, p.rs);
-    const float bias_m = (p.bias && p.bias_on_m) ? p.bias[m] : 0.f;
-    const int pos = p.pos ? p.pos[m] : 0;
+    const RowCtx rc = epilogue_row(p, c_base, m);
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-      const int n = n0 + g * 64 + tx * 4;
-      if (n >= Nz) continue;
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        float x = acc[i][g * 4 + j] * p.alpha;
-        if (p.bias) x += p.bias_on_m ? bias_m : ((n + j < Nz) ? p.bias[n + j] : 0.f);
-        if (p.act == 1) x = gelu_erf(x);
-        v[j] = x;
-      }
-      if (p.pos && n < p.rope_cols) {
-        const int d = n % p.head_dim;  // head offsets are multiples of 4, pairs never straddle
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int dd = d + 2 * q;
-          if (dd < p.rot_dim) {
-            const float c = p.rope_cos[(int64_t)pos * half_rot + (dd >> 1)];
-            const float s = p.rope_sin[(int64_t)pos * half_rot + (dd >> 1)];
-            const float x0 = v[2 * q], x1 = v[2 * q + 1];
-            v[2 * q] = x0 * c - x1 * s;
-            v[2 * q + 1] = x1 * c + x0 * s;
-          }
-        }
-      }
-      const int64_t c0 = split_off(n, p.cm1, p.cm2, p.cs1, p.cs2, 1);
-      const bool full = (n + 3 < Nz);
-      const bool contig = full && (p.cm1 == 0 || ((n % p.cm2) + 3 < p.cm2));
-      const int64_t addr = roff + c0;
-      if (p.out_half) {
-        __half* C = reinterpret_cast<__half*>(p.C);
-        if (contig && (addr & 3) == 0) {
-          __half2 h0 = __floats2half2_rn(v[0], v[1]);
-          __half2 h1 = __floats2half2_rn(v[2], v[3]);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(C + addr) = u;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (n + j < Nz)
-              C[roff + split_off(n + j, p.cm1, p.cm2, p.cs1, p.cs2, 1)] = __float2half_rn(v[j]);
-        }
-      } else {
-        float* C = reinterpret_cast<float*>(p.C);
-        if (contig && (addr & 3) == 0) {
-          float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.accumulate) {
-            float4 old = *reinterpret_cast<const float4*>(C + addr);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(C + addr) = o;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (n + j < Nz) {
-              const int64_t a2 = roff + split_off(n + j, p.cm1, p.cm2, p.cs1, p.cs2, 1);
-              C[a2] = p.accumulate ? C[a2] + v[j] : v[j];
-            }
-        }
-      }
-    }
+    for (int g = 0; g < 2; g++) epilogue_store4(p, rc, n0 + g * 64 + tx * 4, Nz, &acc[i][g * 4]);
   }
 }
 
 }  // namespace
 
-void launch_gemm(const GemmParams& p, cudaStream_t stream) {
+void launch_gemm_simt(const GemmParams& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.groups <= 0) return;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.groups);
   gemm_nt_kernel<<<grid, 256, 0, stream>>>(p);

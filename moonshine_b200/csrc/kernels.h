@@ -48,7 +48,11 @@ struct GemmParams {
   const float* rope_sin = nullptr;
   int rope_cols = 0, head_dim = 1, rot_dim = 0;
 };
+// Dispatches to the tcgen05 bf16x3 kernel (default) or the fp32 SIMT kernel
+// (MOONSHINE_B200_GEMM=simt).
 void launch_gemm(const GemmParams& p, cudaStream_t stream);
+void launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
+void launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // Frontend
@@ -108,6 +112,9 @@ struct DecoderParams {
   DecLayerWeights layers[kMaxDecLayers];
   const float* embed;     // [V][D]   (gather)
   const float* embT;      // [D][V]   (tied logits head, k-major)
+  const float* embS;      // [n_vchunk][D][vchunk] per-chunk slabs of embT (v2 kernel)
+  int smem_limit;         // opt-in shared memory per CTA (v2 ring sizing)
+  void* prof;             // optional [grid][512] u64 timestamps (v2 kernel, debugging)
   const float* final_ln;  // [D]
   const float* rope_cos;  // [Smax][rot/2]
   const float* rope_sin;
@@ -131,6 +138,9 @@ struct DecoderParams {
   unsigned int* barrier;  // [2] grid barrier state
 };
 void launch_decoder_step(const DecoderParams& p, int grid, cudaStream_t stream);
+// v2: operands streamed through a TMA-bulk smem ring by a producer warp.
+void launch_decoder_step2(const DecoderParams& p, int grid, cudaStream_t stream);
+size_t decoder_step2_smem_bytes(const DecoderParams& p);
 void decoder_tiles_for_batch(int B, int& nb_attn, int& nb_mlp);
 size_t decoder_step_smem_bytes(const DecoderParams& p);
 // Resolves the last step's argmax into tokens[] (the step kernel resolves the

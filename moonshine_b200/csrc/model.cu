@@ -46,6 +46,18 @@ Model::Model(const Dims& dims, const WeightFile& weights, int device) : d_(dims)
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   for (auto& e : ev_) CUDA_CHECK(cudaEventCreate(&e));
   if (d_.dec_layers > kMaxDecLayers) throw std::runtime_error("too many decoder layers");
+  {
+    int per = (d_.vocab + sm_count_ - 1) / sm_count_;
+    per = round_up(std::max(per, 32), 32);
+    if (per > 256) per = 256;
+    vchunk_ = per;
+    n_vchunk_ = (d_.vocab + per - 1) / per;
+  }
+  CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+  {
+    const char* e = std::getenv("MOONSHINE_B200_DECODER");
+    decoder_v2_ = !(e && std::string(e) == "v1");
+  }
   build_weights(weights);
   barrier_.reserve(2);
   CUDA_CHECK(cudaMemsetAsync(barrier_.ptr, 0, 2 * sizeof(unsigned), stream_));
@@ -125,6 +137,13 @@ void Model::build_weights(const WeightFile& wf) {
   size_t o_embT = bb.add((size_t)D * V);
   for (int v = 0; v < V; v++)
     for (int k = 0; k < D; k++) bb.data[o_embT + (size_t)k * V + v] = emb[(size_t)v * D + k];
+  // per-vocab-chunk slabs [n_vchunk][D][vchunk] (zero padded) for the streamed logits phase
+  size_t o_embS = bb.add((size_t)n_vchunk_ * D * vchunk_);
+  for (int v = 0; v < V; v++) {
+    const int ch = v / vchunk_, j = v % vchunk_;
+    for (int k = 0; k < D; k++)
+      bb.data[o_embS + ((size_t)ch * D + k) * vchunk_ + j] = emb[(size_t)v * D + k];
+  }
   size_t o_decln = bb.add_copy(wf.get(dd + "norm.weight", {D}).data, D);
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
   size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
@@ -213,6 +232,7 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
+  dec_.embS = base + o_embS; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   for (int l = 0; l < d_.dec_layers; l++) {
     DecLayerWeights& w = dec_.layers[l];
     w.ln1 = base + dof[l].ln1; w.wqkv = base + dof[l].wqkv; w.wo = base + dof[l].wo;
@@ -520,14 +540,6 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   // ---------------- greedy decode ----------------
   DecoderParams p = dec_;
   p.B = B; p.Tpad = Tpad; p.Smax = Smax;
-  p.n_vchunk = 0;
-  {
-    int per = (V + sm_count_ - 1) / sm_count_;
-    per = round_up(std::max(per, 32), 32);
-    if (per > 256) per = 256;
-    p.vchunk = per;
-    p.n_vchunk = (V + per - 1) / per;
-  }
   const size_t self_elems = (size_t)L * B * H * hd * Smax;
   ks_.reserve(self_elems);
   vs_.reserve(self_elems);
@@ -581,11 +593,34 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     CUDA_CHECK(cudaMemsetAsync(logits_dbg_.ptr, 0, (size_t)dbg_steps * B * V * sizeof(float), stream_));
   }
   const int grid = sm_count_;
+  // v2 streams operands through the smem ring; its cross-attention maps one thread to 4 key
+  // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
+  const bool use_v2 = decoder_v2_ && Tpad <= 1024;
+  static const int prof_step = std::getenv("MOONSHINE_B200_PROF") ? std::atoi(std::getenv("MOONSHINE_B200_PROF")) : -1;
+  DeviceBuffer<unsigned long long> prof_buf;
+  if (prof_step >= 0) {
+    prof_buf.reserve((size_t)grid * 512);
+    CUDA_CHECK(cudaMemsetAsync(prof_buf.ptr, 0, prof_buf.bytes(), stream_));
+  }
   for (int t = 0; t < max_steps; t++) {
     p.step = t;
+    p.prof = (t == prof_step) ? (void*)prof_buf.ptr : nullptr;
     p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
-    launch_decoder_step(p, grid, stream_);
+    if (use_v2) launch_decoder_step2(p, grid, stream_);
+    else launch_decoder_step(p, grid, stream_);
     stage("decoder_step", t, 16);
+  }
+  if (prof_step >= 0) {
+    std::vector<unsigned long long> h((size_t)grid * 512);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaMemcpy(h.data(), prof_buf.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (int cta : {0, 1, 77, 127, 140, 147}) {
+      if (cta >= grid) continue;
+      fprintf(stderr, "PROF cta %d:", cta);
+      for (int i = 0; i < 512 && h[(size_t)cta * 512 + i]; i++)
+        fprintf(stderr, " %u:%llu", (unsigned)(h[(size_t)cta * 512 + i] & 255), (h[(size_t)cta * 512 + i] >> 8) - (h[(size_t)cta * 512] >> 8));
+      fprintf(stderr, "\n");
+    }
   }
   p.step = max_steps;
   launch_decoder_finalize(p, stream_);

@@ -84,6 +84,8 @@ class Model {
   const float *wk_all_ = nullptr, *wv_all_ = nullptr;
   DecoderParams dec_{};  // weight pointers + dims prefilled
   int ffn_chunk_ = 64;
+  int vchunk_ = 0, n_vchunk_ = 0, smem_optin_ = 0;
+  bool decoder_v2_ = true;
 
   // rope tables (grow-only)
   DeviceBuffer<float> rope_cos_, rope_sin_;

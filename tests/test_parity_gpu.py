@@ -180,17 +180,29 @@ def test_too_short_audio_is_an_error_not_a_crash():
     t.close()
 
 
-def test_gemm_kernel_against_torch():
+@pytest.mark.parametrize("impl,tol", [(1, 1e-5), (2, 6e-5)], ids=["simt_fp32", "tcgen05_bf16x3"])
+def test_gemm_kernel_against_torch(impl, tol):
+    """Both dense kernels against a float64 torch reference (bias + exact GELU
+    epilogue, ragged M/N/K incl. K % 32 != 0 and K % 4 != 0 handled by padding)."""
     import torch
     lib = api.load_library()
     torch.manual_seed(0)
-    for (M, N, K) in [(300, 200, 52), (129, 257, 36), (1000, 576, 2016), (415, 415, 416)]:
+    for (M, N, K) in [(300, 200, 52), (129, 257, 36), (1000, 576, 2016), (415, 415, 416), (128, 128, 32),
+                      (77, 130, 288), (2049, 96, 1152)]:
         A = torch.randn(M, K, device="cuda")
         W = torch.randn(N, K, device="cuda")
         bias = torch.randn(N, device="cuda")
         C = torch.zeros(M, N, device="cuda")
         rc = lib.moonshine_b200_test_gemm(A.data_ptr(), W.data_ptr(), C.data_ptr(), M, N, K, K, K, N,
-                                          bias.data_ptr(), 1, 0, 0)
+                                          bias.data_ptr(), 1, 0, impl)
         assert rc == 0
         ref = torch.nn.functional.gelu(A.double() @ W.double().T + bias.double()).float()
-        assert (C - ref).abs().max().item() / ref.abs().max().item() < 1e-5
+        err = (C - ref).abs().max().item() / ref.abs().max().item()
+        assert err < tol, (M, N, K, err)
+        # accumulate mode, no activation
+        C2 = torch.ones(M, N, device="cuda")
+        rc = lib.moonshine_b200_test_gemm(A.data_ptr(), W.data_ptr(), C2.data_ptr(), M, N, K, K, K, N,
+                                          0, 0, 1, impl)
+        assert rc == 0
+        ref2 = (1.0 + A.double() @ W.double().T).float()
+        assert (C2 - ref2).abs().max().item() / ref2.abs().max().item() < tol
