@@ -29,11 +29,13 @@ namespace msb {
 namespace {
 
 constexpr int TM = 128, TN = 128, TK = 32;
-constexpr int kStages = 3;
+constexpr int kStages = 1;                     // bf16 operand stages (UMMA-ready)
+constexpr int kRawStages = 2;                  // fp32 staging ring filled by cp.async
 constexpr int kLoaders = 256;
 constexpr int kThreadsTC = kLoaders + 32;
 constexpr int kTileBytes = TM * TK * 2;        // one bf16 plane of one operand: 8 KB
 constexpr int kStageBytesTC = 4 * kTileBytes;  // A_hi, A_lo, W_hi, W_lo
+constexpr int kRawBytes = 2 * TM * TK * 4;     // A and W fp32 tiles of one K block: 32 KB
 constexpr int kTmemCols = 128;
 constexpr long long kSpinLimitTC = 4000000000LL;
 
@@ -103,7 +105,7 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
 
-__global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p, const int dbg) {
   const int z = blockIdx.z;
   const int Mz = p.Mz ? p.Mz[z] : p.M;
   const int Nz = p.Nz ? p.Nz[z] : p.N;
@@ -155,18 +157,41 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
     const int ld = is_w ? p.ldw : p.lda;
     const int row0 = is_w ? n0 : m0;
     const int rows_valid = is_w ? Nz : Mz;
-    // swizzled byte offset of this thread's 8-byte slot inside an 8 KB plane, per pass
-    // row r (pitch 64 B), 16-byte chunk c = q >> 1 stored at c ^ ((r >> 1) & 3)
+    // Each thread owns 8 fixed 16-byte chunks (row i*16+rsub, float4 q) of its operand tile:
+    // it cp.asyncs them into the raw fp32 ring, later reads the same chunks back, splits them
+    // to bf16 hi/lo and stores them K-major SWIZZLE_64B (row pitch 64 B, 16-byte chunk
+    // c = q >> 1 stored at c ^ ((r >> 1) & 3)).  No cross-thread hazards on the raw ring.
+    unsigned char* raw_base = smem + (size_t)kStages * kStageBytesTC + (is_w ? TM * TK * 4 : 0);
+    auto issue = [&](int kb) {
+      const int k = kb * TK + q * 4;
+      unsigned char* dst = raw_base + (size_t)(kb % kRawStages) * kRawBytes;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int rl = i * 16 + rsub;
+        const int r = row0 + rl;
+        if (r < rows_valid && k < Kz && !(dbg & 2)) {
+          const uint32_t d = smem_u32(dst + rl * 128 + q * 16);
+          const float* g = src + (int64_t)r * ld + k;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    if (nk > 1) issue(1); else asm volatile("cp.async.commit_group;" ::: "memory");
     for (int kb = 0; kb < nk; kb++) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)((kb / kStages) & 1);
       const int k = kb * TK + q * 4;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's chunks of block kb landed
+      const unsigned char* rsrc = raw_base + (size_t)(kb % kRawStages) * kRawBytes;
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const int r = row0 + i * 16 + rsub;
-        if (r < rows_valid && k < Kz) {
-          v[i] = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + k);
+        const int rl = i * 16 + rsub;
+        const int r = row0 + rl;
+        if (r < rows_valid && k < Kz && !(dbg & 2)) {
+          v[i] = *reinterpret_cast<const float4*>(rsrc + rl * 128 + q * 16);
           if (k + 3 >= Kz) {  // K tail inside the float4: row padding must not contribute
             if (k + 1 >= Kz) v[i].y = 0.f;
             if (k + 2 >= Kz) v[i].z = 0.f;
@@ -176,18 +201,22 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      mbar_wait(&empty_bar[s], ph ^ 1u);  // MMAs that read this stage have completed
+      uint2 hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) split4(v[i], hi[i], lo[i]);
+      // the reads above have been consumed: refill the raw slot just drained
+      if (kb + kRawStages < nk) issue(kb + kRawStages);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      mbar_wait(&empty_bar[s], ph ^ 1u);  // MMAs that read this bf16 stage have completed
       unsigned char* stage = smem + (size_t)s * kStageBytesTC + (is_w ? 2 * kTileBytes : 0);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int r = i * 16 + rsub;
         const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)q >> 1) ^ (((uint32_t)r >> 1) & 3u)) << 4) + ((uint32_t)q & 1u) * 8u;
-        uint2 hi, lo;
-        split4(v[i], hi, lo);
-        *reinterpret_cast<uint2*>(stage + off) = hi;
-        *reinterpret_cast<uint2*>(stage + kTileBytes + off) = lo;
+        *reinterpret_cast<uint2*>(stage + off) = hi[i];
+        *reinterpret_cast<uint2*>(stage + kTileBytes + off) = lo[i];
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+      if (!(dbg & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(&full_bar[s]);
     }
   } else if (tid == kLoaders) {
@@ -215,20 +244,24 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
     umma_commit(&accum_bar);       // accumulator complete
   }
 
-  // ============================ epilogue (warps 0-3) ============================
-  if (warp < 4) {
+  // ============================ epilogue (warps 0-7) ============================
+  // TMEM -> registers -> shared (row pitch 132 floats, conflict-free) -> coalesced row-wise
+  // stores: 16 lanes cover 64 contiguous columns of one output row.  The staging area reuses
+  // the operand ring, which is idle once the accumulator barrier has fired.
+  if (warp < 8 && !(dbg & 4)) {
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int64_t c_base = p.offC ? p.offC[z] : (int64_t)z * p.strideC;
     const int lane = tid & 31;
-    const int m = m0 + warp * 32 + lane;         // TMEM lane == output row
-    RowCtx rc = {0, 0.f, 0};
-    if (m < Mz) rc = epilogue_row(p, c_base, m);
+    const int wq = warp & 3;                     // TMEM lane quarter this warp may access
+    const int chalf = warp >> 2;                 // warps 0-3: columns 0-63, warps 4-7: 64-127
+    constexpr int kPitch = 132;
+    float* stage = reinterpret_cast<float*>(smem);   // [128][132] floats = 67.6 KB <= 96 KB ring
 #pragma unroll 1
-    for (int cb = 0; cb < TN / 32; cb++) {
+    for (int cb = chalf * 2; cb < chalf * 2 + 2; cb++) {
       if (n0 + cb * 32 >= Nz) break;            // uniform
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cb * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -240,13 +273,25 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < Mz) {
+      float* dst = stage + (wq * 32 + lane) * kPitch + cb * 32;
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-          float acc[4] = {__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                          __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])};
-          epilogue_store4(p, rc, n0 + cb * 32 + g * 4, Nz, acc);
-        }
+      for (int g = 0; g < 8; g++)
+        *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                                              __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+    }
+    __syncwarp();
+    // this warp staged rows [wq*32, wq*32+32) x columns [chalf*64, chalf*64+64): drain them row-wise
+    const int n4 = lane & 15;
+    const int n = n0 + chalf * 64 + n4 * 4;
+#pragma unroll 4
+    for (int it = 0; it < 16; it++) {
+      const int rl = wq * 32 + it * 2 + (lane >> 4);
+      const int m = m0 + rl;
+      if (m < Mz && n < Nz) {
+        const RowCtx rc = epilogue_row(p, c_base, m);
+        const float4 a = *reinterpret_cast<const float4*>(stage + rl * kPitch + chalf * 64 + n4 * 4);
+        const float acc[4] = {a.x, a.y, a.z, a.w};
+        epilogue_store4(p, rc, n, Nz, acc);
       }
     }
   }
@@ -262,13 +307,14 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
 void launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.groups <= 0) return;
   static bool configured = false;
-  const size_t smem = (size_t)kStages * kStageBytesTC + 1024;
+  const size_t smem = (size_t)kStages * kStageBytesTC + (size_t)kRawStages * kRawBytes + 1024;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, p.groups);
-  gemm_tc_kernel<<<grid, kThreadsTC, smem, stream>>>(p);
+  static const int dbg = std::getenv("MOONSHINE_B200_GEMM_DBG") ? std::atoi(std::getenv("MOONSHINE_B200_GEMM_DBG")) : 0;
+  gemm_tc_kernel<<<grid, kThreadsTC, smem, stream>>>(p, dbg);
 }
 
 void launch_gemm(const GemmParams& p, cudaStream_t stream) {
