@@ -10,6 +10,7 @@
 // but never waits for the grid barriers, so the HBM/L2 stream runs ahead of the
 // dependency chain and the consumers only ever touch shared memory, plus the
 // small activation / partial-sum exchanges through L2.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.h"
@@ -111,9 +112,11 @@ struct Ring {
     mbar_wait(&full[stage()], parity());
     return data + (size_t)stage() * kStageBytes;
   }
-  // call after every consumer finished reading the stage (i.e. after csync())
+  // every consumer WARP releases the stage once its lanes are done reading it
+  // (empty barriers count kWarpsC arrivals): no CTA-wide sync per chunk.
   __device__ __forceinline__ void release() {
-    if (threadIdx.x == 0) mbar_arrive(&empty[stage()]);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage()]);
     idx++;
   }
   // producer (one lane)
@@ -138,8 +141,8 @@ __device__ __forceinline__ int rows_per_chunk_f16(int rows, int cols) {
 }
 
 struct SmemLayout2 {
-  int hs, xs, act, att, red, ps, sc, flags, argv, argi, active, bars, ring;  // byte offsets
-  int actw, attw, total, ns;
+  int hs, xs, act, att, red, ps, sc, flags, argv, argi, active, bars, ring, rope, bias;  // byte offsets
+  int actw, attw, total, ns, xpitch;
 };
 
 __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int hd, int IC, int Tpad,
@@ -155,14 +158,19 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
   L.att = take(NBmax * L.attw * 4);
   // split-K scratch only for small tiles (NB <= 4); larger tiles use the row-split mapping
   int red = (NBmax <= 4 ? 1024 * NBmax : 0) * 4;
-  if (red < D * kLogitsTile * 4) red = D * kLogitsTile * 4;
-  if (red < 2 * 528 * 4) red = 2 * 528 * 4;
+  if (red < (16 + 1024) * 4) red = (16 + 1024) * 4;
   L.red = take(red);
+  // the logits phase aliases [0, xg_bytes) with its 32 x xpitch x-tile (xpitch % 32 == 8)
+  L.xpitch = D + ((8 - (D % 32)) + 32) % 32;
+  const int xg_bytes = kLogitsTile * L.xpitch * 4;
+  if (o < xg_bytes) o = (xg_bytes + 15) / 16 * 16;
   L.ps = take(Tpad * 4);
-  L.sc = take(kWarpsC * Smax * 4);
+  L.sc = take(kWarpsC * (Smax + 4) * 4);
   L.flags = take(64 * 4);
   L.argv = take(kWarpsC * kLogitsTile * 4);
   L.argi = take(kWarpsC * kLogitsTile * 4);
+  L.rope = take(128 * 4);
+  L.bias = take(2 * IC * 4);
   L.active = take(B);
   L.bars = take(2 * 16 * 8);
   o = (o + 127) / 128 * 128;
@@ -176,6 +184,10 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
 
 constexpr int kProfSlots = 512;
 struct Ctx {
+  const float* rope;         // smem: cos[0..64) | sin[64..128) of this step's position
+  float* bias;               // smem: staged FC1 bias chunk (2 * IC floats)
+  float* xg;                 // smem: [32][xpitch] final-LN rows for the logits phase (aliases hs..red)
+  int xpitch;
   unsigned long long* prof;  // optional [grid][kProfSlots] globaltimer stamps (thread 0)
   int prof_n;
   float *hs, *xs, *act, *att, *red, *ps, *sc, *argv;
@@ -230,7 +242,6 @@ __device__ __forceinline__ void gemm_ring_splitk(Ring& ring, const float* x, int
         }
       }
     }
-    csync();
     ring.release();
   }
   if (on) {
@@ -284,7 +295,6 @@ __device__ __forceinline__ void gemm_ring_rows(Ring& ring, const float* x, int l
         }
       }
     }
-    csync();
     ring.release();
   }
   if (on) {
@@ -332,8 +342,10 @@ __device__ __forceinline__ void produce_block_f16(Ring& ring, const __half* M, i
   }
 }
 
-__device__ __forceinline__ void layernorm_rows(const float* hs, float* xs,
-                                               const float* __restrict__ gamma, int nb, int D) {
+// LayerNorm WITHOUT the affine weight: gamma is folded into the rows of the
+// following weight block at load time (Model::build_weights), so the dependency
+// chain holds no global load here.
+__device__ __forceinline__ void layernorm_rows(const float* hs, float* xs, int nb, int D) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = w; b < nb; b += kWarpsC) {
     const float* h = hs + b * D;
@@ -346,7 +358,7 @@ __device__ __forceinline__ void layernorm_rows(const float* hs, float* xs,
       q += d * d;
     }
     const float rstd = rsqrtf(warp_sum(q) / D + 1e-5f);
-    for (int c = lane; c < D; c += 32) xs[b * D + c] = (h[c] - mean) * rstd * gamma[c];
+    for (int c = lane; c < D; c += 32) xs[b * D + c] = (h[c] - mean) * rstd;
   }
   csync();
 }
@@ -399,10 +411,12 @@ __device__ __forceinline__ int step_prologue_warp(const DecoderParams& p, int b,
   return tok_in;
 }
 
-__device__ __forceinline__ void load_flags(const DecoderParams& p, const Ctx& c, int NB, int b0) {
+__device__ __forceinline__ void load_flags(const DecoderParams& p, const Ctx& c, int NB, int b0,
+                                           bool with_enc_len = false) {
   if (threadIdx.x < NB) {
     const int b = b0 + threadIdx.x;
     c.flags[threadIdx.x] = (b < p.B) ? (c.active[b] ? 0 : 1) : 1;
+    if (with_enc_len) c.flags[32 + threadIdx.x] = (b < p.B) ? p.enc_len[b] : 0;
   }
   csync();
 }
@@ -424,8 +438,18 @@ __device__ __forceinline__ void resolve_rows(const DecoderParams& p, const Ctx& 
     if (!c.flags[b]) {
       const int64_t r = (int64_t)(b0 + b) * D4 + c4;
       v = reinterpret_cast<const float4*>(hrd)[r];
-      for (int j = 0; j < nparts; j++) {
-        const float4 q = reinterpret_cast<const float4*>(part)[(int64_t)j * p.B * D4 + r];
+      const float4* pp = reinterpret_cast<const float4*>(part) + r;
+      const int64_t pstride = (int64_t)p.B * D4;
+      int j = 0;
+      for (; j + 8 <= nparts; j += 8) {  // 8 independent loads in flight, summed in order
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) q[u] = pp[(int64_t)(j + u) * pstride];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { v.x += q[u].x; v.y += q[u].y; v.z += q[u].z; v.w += q[u].w; }
+      }
+      for (; j < nparts; j++) {
+        const float4 q = pp[(int64_t)j * pstride];
         v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
       }
       if (bias) {
@@ -504,7 +528,7 @@ __device__ void phase_self(const DecoderParams& p, int l, int item, Ctx& c, Ring
     resolve_rows(p, c, NB, b0, hrd, hwr, partC, p.n_chunk, p.layers[l - 1].b2, h == 0);
   }
   prof_mark(c, 1);
-  layernorm_rows(c.hs, c.xs, w.ln1, NB, D);
+  layernorm_rows(c.hs, c.xs, NB, D);
   prof_mark(c, 2);
   gemm_ring<NB>(ring, c, c.xs, D, D, 3 * hd, nullptr, c.act, actw);
   prof_mark(c, 3);
@@ -516,8 +540,8 @@ __device__ void phase_self(const DecoderParams& p, int l, int item, Ctx& c, Ring
       const int r = i - b * 2 * half_rot;
       const int which = r / half_rot;
       const int pr = r - which * half_rot;
-      const float cs = p.rope_cos[(int64_t)p.step * half_rot + pr];
-      const float sn = p.rope_sin[(int64_t)p.step * half_rot + pr];
+      const float cs = c.rope[pr];
+      const float sn = c.rope[64 + pr];
       float* v = c.act + b * actw + which * hd + 2 * pr;
       const float x0 = v[0], x1 = v[1];
       v[0] = x0 * cs - x1 * sn;
@@ -533,69 +557,79 @@ __device__ void phase_self(const DecoderParams& p, int l, int item, Ctx& c, Ring
       p.vs[(bh * p.Smax + p.step) * hd + d] = c.act[b * actw + 2 * hd + d];
     }
   }
-  // causal self-attention, one utterance at a time (cache chunks arrive in order)
+  // causal self-attention: ONE WARP per utterance (round-robin), warp-level syncs only.
+  // Cache chunks arrive in utterance order; every warp acquires / releases every chunk (the
+  // ring is CTA-wide) but only the owner warp computes on it, so utterances overlap.
   const float scale = rsqrtf((float)hd);
-  for (int b = 0; b < NB; b++) {
-    if (c.flags[b]) continue;  // uniform
-    const float* q = c.act + b * actw;
-    const float* kcur = q + hd;
-    const float* vcur = q + 2 * hd;
-    float* sc = c.sc;
-    // scores: thread t owns key position t (cache positions < step arrive as
-    // row chunks of the staged K^T; position `step` is the k just computed)
-    for (int t = threadIdx.x; t <= p.step; t += kConsumers) sc[t] = 0.f;
-    csync();
-    if (p.step > 0) {
-      const int rpc = rows_per_chunk_f32(hd, p.Smax);
-      for (int d0 = 0; d0 < hd; d0 += rpc) {
-        const int nd = min(rpc, hd - d0);
-        const float* Kc = reinterpret_cast<const float*>(ring.acquire());
-        for (int t = threadIdx.x; t < p.step; t += kConsumers) {
-          float s = sc[t];
-          for (int d = 0; d < nd; d++) s = fmaf(q[d0 + d], Kc[d * p.Smax + t], s);
-          sc[t] = s;
+  {
+    float* sc = c.sc + warp * (p.Smax + 4);
+    int owner = 0;
+    for (int b = 0; b < NB; b++) {
+      if (c.flags[b]) continue;  // uniform
+      const bool mine = (owner == warp);
+      owner = (owner + 1) & (kWarpsC - 1);
+      const float* q = c.act + b * actw;
+      const float* kcur = q + hd;
+      const float* vcur = q + 2 * hd;
+      // scores: lane owns key positions t = lane, lane+32, ...
+      if (mine)
+        for (int t = lane; t <= p.step; t += 32) sc[t] = 0.f;
+      if (p.step > 0) {
+        const int rpc = rows_per_chunk_f32(hd, p.Smax);
+        for (int d0 = 0; d0 < hd; d0 += rpc) {
+          const int nd = min(rpc, hd - d0);
+          const float* Kc = reinterpret_cast<const float*>(ring.acquire());
+          if (mine) {
+            for (int t = lane; t < p.step; t += 32) {
+              float s = sc[t];
+              for (int d = 0; d < nd; d++) s = fmaf(q[d0 + d], Kc[d * p.Smax + t], s);
+              sc[t] = s;
+            }
+          }
+          ring.release();
         }
-        csync();
-        ring.release();
+      }
+      float inv = 0.f;
+      if (mine) {
+        float s = 0.f;
+        for (int d = lane; d < hd; d += 32) s = fmaf(q[d], kcur[d], s);
+        s = warp_sum(s);
+        if (lane == 0) sc[p.step] = s;
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int t = lane; t <= p.step; t += 32) mx = fmaxf(mx, sc[t] * scale);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int t = lane; t <= p.step; t += 32) {
+          const float e = expf(sc[t] * scale - mx);
+          sc[t] = e;
+          sum += e;
+        }
+        inv = 1.0f / warp_sum(sum);
+        __syncwarp();
+      }
+      float o0 = 0.f, o1 = 0.f;  // lane owns dims d = lane, lane + 32 (hd <= 64)
+      if (p.step > 0) {
+        const int rpc = rows_per_chunk_f32(p.step, hd);
+        for (int r0 = 0; r0 < p.step; r0 += rpc) {
+          const int nr = min(rpc, p.step - r0);
+          const float* Vc = reinterpret_cast<const float*>(ring.acquire());
+          if (mine) {
+            for (int t = 0; t < nr; t++) {
+              const float pt = sc[r0 + t];
+              if (lane < hd) o0 = fmaf(pt, Vc[t * hd + lane], o0);
+              if (lane + 32 < hd) o1 = fmaf(pt, Vc[t * hd + lane + 32], o1);
+            }
+          }
+          ring.release();
+        }
+      }
+      if (mine) {
+        const float pl = sc[p.step];
+        if (lane < hd) c.att[b * attw + lane] = fmaf(pl, vcur[lane], o0) * inv;
+        if (lane + 32 < hd) c.att[b * attw + lane + 32] = fmaf(pl, vcur[lane + 32], o1) * inv;
       }
     }
-    if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int d = 0; d < hd; d++) s = fmaf(q[d], kcur[d], s);
-      sc[p.step] = s;
-    }
-    csync();
-    if (warp == 0) {  // softmax over step+1 scores
-      float mx = -INFINITY;
-      for (int t = lane; t <= p.step; t += 32) mx = fmaxf(mx, sc[t] * scale);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int t = lane; t <= p.step; t += 32) {
-        const float e = expf(sc[t] * scale - mx);
-        sc[t] = e;
-        sum += e;
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) sc[p.step + 1] = 1.0f / sum;  // sc holds kWarpsC * Smax >= step + 2 floats
-    }
-    csync();
-    float o = 0.f;
-    if (p.step > 0) {
-      const int rpc = rows_per_chunk_f32(p.step, hd);
-      for (int r0 = 0; r0 < p.step; r0 += rpc) {
-        const int nr = min(rpc, p.step - r0);
-        const float* Vc = reinterpret_cast<const float*>(ring.acquire());
-        if (threadIdx.x < hd)
-          for (int t = 0; t < nr; t++) o = fmaf(sc[r0 + t], Vc[t * hd + threadIdx.x], o);
-        csync();
-        ring.release();
-      }
-    }
-    if (threadIdx.x < hd) {
-      o = fmaf(sc[p.step], vcur[threadIdx.x], o);
-      c.att[b * attw + threadIdx.x] = o * sc[p.step + 1];
-    }
-    csync();
   }
   csync();
   prof_mark(c, 4);
@@ -633,10 +667,10 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int actw = c.actw, attw = c.attw;
 
-  load_flags(p, c, NB, b0);
+  load_flags(p, c, NB, b0, true);
   resolve_rows(p, c, NB, b0, hrd, hwr, partA, H, nullptr, h == 0);
   prof_mark(c, 11);
-  layernorm_rows(c.hs, c.xs, w.ln2, NB, D);
+  layernorm_rows(c.hs, c.xs, NB, D);
   prof_mark(c, 12);
   gemm_ring<NB>(ring, c, c.xs, D, D, hd, nullptr, c.act, actw);
   prof_mark(c, 13);
@@ -646,13 +680,15 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
   const int tpr = hd >> 2;           // threads per V row (4 halves = 8 bytes each)
   const int G = kConsumers / tpr;    // V rows per pass
   float* ps = c.ps;
-  float* redw = c.red;               // [8] warp partials, then [G][hd] PV partials
+  float* red_max = c.red;            // [8] warp maxima
+  float* red_sum = c.red + 8;        // [8] warp sums
+  float* pv = c.red + 16;            // [G][hd] PV partials (G * hd <= 1024)
   for (int b = 0; b < NB; b++) {
     if (c.flags[b]) continue;  // uniform
-    const int T = p.enc_len[b0 + b];
+    const int T = c.flags[32 + b];   // encoder length, staged by load_flags
     const float* q = c.act + b * actw;
-    // ---- scores over K^T chunks (rows = head dims) ----
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // thread j: t = 4j .. 4j+3 (Tpad <= 1024)
+    // ---- scores over K^T chunks (rows = head dims); thread j owns t = 4j .. 4j+3 ----
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const int t4 = threadIdx.x * 4;
     {
       const int rpc = rows_per_chunk_f16(hd, Tpad);
@@ -672,7 +708,6 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
             s3 = fmaf(qd, f1.y, s3);
           }
         }
-        csync();
         ring.release();
       }
     }
@@ -685,29 +720,28 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
       lmax = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
     }
     lmax = warp_max(lmax);
-    if (lane == 0) redw[warp] = lmax;
-    csync();
-    float mx = redw[0];
+    if (lane == 0) red_max[warp] = lmax;
+    csync();                                   // (1) maxima visible; previous utterance fully done
+    float mx = red_max[0];
 #pragma unroll
-    for (int i = 1; i < kWarpsC; i++) mx = fmaxf(mx, redw[i]);
+    for (int i = 1; i < kWarpsC; i++) mx = fmaxf(mx, red_max[i]);
     float lsum = 0.f;
     if (t4 < Tpad) {
       s0 = (t4 + 0 < T) ? expf(s0 - mx) : 0.f;
       s1 = (t4 + 1 < T) ? expf(s1 - mx) : 0.f;
       s2 = (t4 + 2 < T) ? expf(s2 - mx) : 0.f;
       s3 = (t4 + 3 < T) ? expf(s3 - mx) : 0.f;
-      ps[t4 + 0] = s0; ps[t4 + 1] = s1; ps[t4 + 2] = s2; ps[t4 + 3] = s3;
+      *reinterpret_cast<float4*>(&ps[t4]) = make_float4(s0, s1, s2, s3);
       lsum = (s0 + s1) + (s2 + s3);
     }
     lsum = warp_sum(lsum);
-    csync();  // everyone has read redw (max); ps visible
-    if (lane == 0) redw[warp] = lsum;
-    csync();
+    if (lane == 0) red_sum[warp] = lsum;
+    csync();                                   // (2) probabilities and sums visible
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWarpsC; i++) tot += redw[i];
+    for (int i = 0; i < kWarpsC; i++) tot += red_sum[i];
     const float inv = 1.0f / tot;
-    // ---- PV over V chunks (rows = time) ----
+    // ---- PV over V chunks (rows = time); thread (g, dq) owns 4 dims of rows g, g+G, ... ----
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const int g = threadIdx.x / tpr, dq = threadIdx.x - g * tpr;
     {
@@ -729,24 +763,18 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
             a3 = fmaf(pt, f1.y, a3);
           }
         }
-        csync();
         ring.release();
       }
     }
-    float* pv = redw + 16;  // [G][hd]  (G * hd <= 1024 floats)
-    if (g < G) {
-      pv[g * hd + dq * 4 + 0] = a0;
-      pv[g * hd + dq * 4 + 1] = a1;
-      pv[g * hd + dq * 4 + 2] = a2;
-      pv[g * hd + dq * 4 + 3] = a3;
-    }
-    csync();
+    if (g < G) *reinterpret_cast<float4*>(&pv[g * hd + dq * 4]) = make_float4(a0, a1, a2, a3);
+    csync();                                   // (3) PV partials visible
     if (threadIdx.x < hd) {
       float o = 0.f;
       for (int gg = 0; gg < G; gg++) o += pv[gg * hd + threadIdx.x];
       c.att[b * attw + threadIdx.x] = o * inv;
     }
-    csync();
+    // no sync here: the next utterance only overwrites red_max before its csync (1), ps after
+    // it and pv after its csync (2) -- by then every thread has left this reduction.
   }
   csync();
   prof_mark(c, 14);
@@ -776,12 +804,13 @@ __device__ void phase_mlp(const DecoderParams& p, int l, int item, Ctx& c, Ring&
   if (!tile_active(p, c.active, NB, b0)) return;
   const DecLayerWeights& w = p.layers[l];
   const int actw = c.actw, attw = c.attw;
+  for (int i = threadIdx.x; i < 2 * IC; i += kConsumers) c.bias[i] = w.b1[(int64_t)ch * 2 * IC + i];
   load_flags(p, c, NB, b0);
   resolve_rows(p, c, NB, b0, hrd, hwr, partB, p.H, nullptr, ch == 0);
   prof_mark(c, 21);
-  layernorm_rows(c.hs, c.xs, w.ln3, NB, D);
+  layernorm_rows(c.hs, c.xs, NB, D);
   prof_mark(c, 22);
-  gemm_ring<NB>(ring, c, c.xs, D, D, 2 * IC, w.b1 + (int64_t)ch * 2 * IC, c.act, actw);
+  gemm_ring<NB>(ring, c, c.xs, D, D, 2 * IC, c.bias, c.act, actw);
   prof_mark(c, 23);
   for (int i = threadIdx.x; i < NB * IC; i += kConsumers) {
     const int b = i / IC, j = i - b * IC;
@@ -804,7 +833,7 @@ __device__ void phase_final_ln(const DecoderParams& p, int item, Ctx& c, const f
   const int b0 = item * NB;
   load_flags(p, c, NB, b0);
   resolve_rows(p, c, NB, b0, hrd, nullptr, partC, p.n_chunk, p.layers[p.L - 1].b2, false);
-  layernorm_rows(c.hs, c.xs, p.final_ln, NB, D);
+  layernorm_rows(c.hs, c.xs, NB, D);
   for (int i = threadIdx.x; i < NB * D; i += kConsumers) {
     const int b = i / D;
     if (b0 + b < p.B) p.xfin[(int64_t)(b0 + b) * D + (i - b * D)] = c.xs[i];
@@ -813,68 +842,136 @@ __device__ void phase_final_ln(const DecoderParams& p, int item, Ctx& c, const f
 }
 
 // ============================== phase G =================================
-// embS: [n_vchunk][D][vchunk] slabs.  One vocab entry per thread.
+// Tied-embedding logits on the tensor cores (mma.sync m16n8k16, bf16x3 split, fp32
+// accumulate): per pass a [32 utterances x D] tile of final-LN rows times the CTA's
+// vocab slab embS[item] = [D][VCP] (k-major, row pitch VCP = vchunk + 4 keeps the
+// B-fragment loads bank-conflict free), streamed through the ring 16 rows (one k-step)
+// at a time.  The per-utterance argmax is fused: no logits leave the SM.
+__device__ __forceinline__ int slab_rows_per_chunk(int vcp) {
+  int r = (kStageBytes / (vcp * 4)) & ~15;
+  return r < 16 ? 16 : r;
+}
 __device__ __forceinline__ void produce_logits(const DecoderParams& p, int item, Ring& ring) {
-  const float* slab = p.embS + (int64_t)item * p.D * p.vchunk;
-  for (int b0 = 0; b0 < p.B; b0 += kLogitsTile) produce_block_f32(ring, slab, p.D, p.vchunk);
+  const float* slab = p.embS + (int64_t)item * p.D * p.vcp;
+  const int rpc = slab_rows_per_chunk(p.vcp);
+  for (int b0 = 0; b0 < p.B; b0 += kLogitsTile)
+    for (int k0 = 0; k0 < p.D; k0 += rpc) {
+      const int rows = min(rpc, p.D - k0);
+      ring.produce(slab + (size_t)k0 * p.vcp, (uint32_t)rows * p.vcp * 4);
+    }
+}
+
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 __device__ void phase_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring) {
-  const int D = p.D, V = p.V, VC = p.vchunk;
-  const int v = item * VC + threadIdx.x;
-  const bool vok = threadIdx.x < VC && v < V;
+  const int D = p.D, V = p.V, VC = p.vchunk, VCP = p.vcp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* xt = c.red;  // [D][kLogitsTile]
+  const int g = lane >> 2, t = lane & 3;
+  const int XP = c.xpitch;
+  float* xg = c.xg;                     // [32][XP] fp32 rows of the final LN
+  const int NT = VC >> 3;               // n-tiles of 8 vocab entries (<= 32)
   const int parity = p.step & 1;
+  const int rpc = slab_rows_per_chunk(VCP);
   for (int b0 = 0; b0 < p.B; b0 += kLogitsTile) {
     const int nb = min(kLogitsTile, p.B - b0);
-    for (int i = threadIdx.x; i < D * kLogitsTile; i += kConsumers) {
-      const int b = i % kLogitsTile, k = i / kLogitsTile;
-      xt[i] = (b < nb) ? p.xfin[(int64_t)(b0 + b) * D + k] : 0.f;
+    for (int i = threadIdx.x; i < kLogitsTile * D; i += kConsumers) {
+      const int b = i / D, k = i - b * D;
+      xg[b * XP + k] = (b < nb) ? p.xfin[(int64_t)(b0 + b) * D + k] : 0.f;
     }
     csync();
-    float acc[kLogitsTile];
+    float acc[2][4][4];
 #pragma unroll
-    for (int b = 0; b < kLogitsTile; b++) acc[b] = 0.f;
-    const int rpc = rows_per_chunk_f32(D, VC);
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
     for (int k0 = 0; k0 < D; k0 += rpc) {
       const int rows = min(rpc, D - k0);
       const float* W = reinterpret_cast<const float*>(ring.acquire());
-      if (threadIdx.x < VC) {
-#pragma unroll 2
-        for (int r = 0; r < rows; r++) {
-          const float wk = W[r * VC + threadIdx.x];
-          const float4* xr = reinterpret_cast<const float4*>(xt + (k0 + r) * kLogitsTile);
+      for (int kk = 0; kk < rows; kk += 16) {   // D % 16 == 0
+        uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
-          for (int b4 = 0; b4 < kLogitsTile / 4; b4++) {
-            const float4 x = xr[b4];
-            acc[b4 * 4 + 0] = fmaf(wk, x.x, acc[b4 * 4 + 0]);
-            acc[b4 * 4 + 1] = fmaf(wk, x.y, acc[b4 * 4 + 1]);
-            acc[b4 * 4 + 2] = fmaf(wk, x.z, acc[b4 * 4 + 2]);
-            acc[b4 * 4 + 3] = fmaf(wk, x.w, acc[b4 * 4 + 3]);
+        for (int mt = 0; mt < 2; mt++) {
+          const float* xr0 = xg + (mt * 16 + g) * XP + k0 + kk + 2 * t;
+          const float* xr1 = xr0 + 8 * XP;
+          const float2 v0 = *reinterpret_cast<const float2*>(xr0);
+          const float2 v1 = *reinterpret_cast<const float2*>(xr1);
+          const float2 v2 = *reinterpret_cast<const float2*>(xr0 + 8);
+          const float2 v3 = *reinterpret_cast<const float2*>(xr1 + 8);
+          split_bf16x2(v0.x, v0.y, ahi[mt][0], alo[mt][0]);
+          split_bf16x2(v1.x, v1.y, ahi[mt][1], alo[mt][1]);
+          split_bf16x2(v2.x, v2.y, ahi[mt][2], alo[mt][2]);
+          split_bf16x2(v3.x, v3.y, ahi[mt][3], alo[mt][3]);
+        }
+        uint32_t bhi[4][2], blo[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int nt = warp + j * kWarpsC;
+          if (nt < NT) {  // warp-uniform
+            const float* wr = W + (kk + 2 * t) * VCP + nt * 8 + g;
+            split_bf16x2(wr[0], wr[VCP], bhi[j][0], blo[j][0]);
+            split_bf16x2(wr[8 * VCP], wr[9 * VCP], bhi[j][1], blo[j][1]);
           }
         }
+        // three split products; within each pass the 8 accumulators are independent
+#pragma unroll
+        for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (warp + j * kWarpsC < NT) {
+#pragma unroll
+              for (int mt = 0; mt < 2; mt++) {
+                if (pass == 0) mma_bf16(acc[mt][j], alo[mt], bhi[j]);
+                else if (pass == 1) mma_bf16(acc[mt][j], ahi[mt], blo[j]);
+                else mma_bf16(acc[mt][j], ahi[mt], bhi[j]);
+              }
+            }
+          }
       }
-      csync();
       ring.release();
     }
-    if (vok && p.logits_out) {
+    // accumulator (mt, j): rows mt*16+g (c0,c1) and +8 (c2,c3), vocab item*VC + nt*8 + 2t (+1)
 #pragma unroll
-      for (int b = 0; b < kLogitsTile; b++)
-        if (b < nb) p.logits_out[(int64_t)(b0 + b) * V + v] = acc[b];
-    }
+    for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
-    for (int b = 0; b < kLogitsTile; b++) {
-      float bv = vok ? acc[b] : -INFINITY;
-      int bi = vok ? v : 0x7fffffff;
-      if (bv != bv) { bv = -INFINITY; bi = 0x7fffffff; }
+      for (int hrow = 0; hrow < 2; hrow++) {
+        const int row = mt * 16 + g + hrow * 8;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        for (int j = 0; j < 4; j++) {
+          const int nt = warp + j * kWarpsC;
+          if (nt < NT) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int v = item * VC + nt * 8 + 2 * t + e;
+              const float x = acc[mt][j][hrow * 2 + e];
+              if (v < V) {
+                if (p.logits_out && row < nb) p.logits_out[(int64_t)(b0 + row) * V + v] = x;
+                if (x > bv || (x == bv && v < bi)) { bv = x; bi = v; }  // NaN never wins
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {  // the 4 lanes of a group share the row
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (t == 0) { c.argv[warp * kLogitsTile + row] = bv; c.argi[warp * kLogitsTile + row] = bi; }
       }
-      if (lane == 0) { c.argv[warp * kLogitsTile + b] = bv; c.argi[warp * kLogitsTile + b] = bi; }
     }
     csync();
     if (threadIdx.x < nb) {
@@ -914,7 +1011,7 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.ns; i++) {
       mbar_init(&ring.full[i], 1);
-      mbar_init(&ring.empty[i], 1);
+      mbar_init(&ring.empty[i], kWarpsC);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -952,6 +1049,18 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   c.active = active;
   c.actw = L.actw;
   c.attw = L.attw;
+  {
+    float* rope = reinterpret_cast<float*>(smem_raw + L.rope);
+    const int half_rot = p.rot_dim >> 1;  // <= 64
+    for (int i = threadIdx.x; i < half_rot; i += kConsumers) {
+      rope[i] = p.rope_cos[(int64_t)p.step * half_rot + i];
+      rope[64 + i] = p.rope_sin[(int64_t)p.step * half_rot + i];
+    }
+    c.rope = rope;
+    c.bias = reinterpret_cast<float*>(smem_raw + L.bias);
+    c.xg = reinterpret_cast<float*>(smem_raw);
+    c.xpitch = L.xpitch;
+  }
   c.prof = reinterpret_cast<unsigned long long*>(p.prof);
   c.prof_n = 0;
   prof_mark(c, 0);
@@ -996,7 +1105,7 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   }
   {
     const float* hrd = p.hbuf + (int64_t)(ph & 1) * BD;
-    for (int it = blockIdx.x; it < n_btm; it += G) phase_final_ln<NBM>(p, it, c, hrd, partC);
+    for (int it = blockIdx.x; it < p.B; it += G) phase_final_ln<1>(p, it, c, hrd, partC);
     prof_mark(c, 31);
     grid_barrier(p.barrier, (++nbar) * G);
     prof_mark(c, 32);

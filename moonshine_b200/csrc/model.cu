@@ -134,17 +134,24 @@ void Model::build_weights(const WeightFile& wf) {
   const std::string dd = "model.decoder.";
   const float* emb = wf.get(dd + "embed_tokens.weight", {V, D}).data;
   size_t o_emb = bb.add_copy(emb, (size_t)V * D);
+  // LayerNorm weights are folded into the rows (k index) of the weight block that consumes the
+  // normalised activations, so the decoder kernels normalise without an affine step:
+  // LN(x) W = ((x - mu) * rstd) (diag(gamma) W).
+  const float* gfin = wf.get(dd + "norm.weight", {D}).data;
+  size_t o_ones = bb.add(D);
+  for (int k = 0; k < D; k++) bb.data[o_ones + k] = 1.0f;
   size_t o_embT = bb.add((size_t)D * V);
   for (int v = 0; v < V; v++)
-    for (int k = 0; k < D; k++) bb.data[o_embT + (size_t)k * V + v] = emb[(size_t)v * D + k];
+    for (int k = 0; k < D; k++) bb.data[o_embT + (size_t)k * V + v] = emb[(size_t)v * D + k] * gfin[k];
   // per-vocab-chunk slabs [n_vchunk][D][vchunk] (zero padded) for the streamed logits phase
-  size_t o_embS = bb.add((size_t)n_vchunk_ * D * vchunk_);
+  const int vcp = vchunk_ + 4;
+  size_t o_embS = bb.add((size_t)n_vchunk_ * D * vcp);
   for (int v = 0; v < V; v++) {
     const int ch = v / vchunk_, j = v % vchunk_;
     for (int k = 0; k < D; k++)
-      bb.data[o_embS + ((size_t)ch * D + k) * vchunk_ + j] = emb[(size_t)v * D + k];
+      bb.data[o_embS + ((size_t)ch * D + k) * vcp + j] = emb[(size_t)v * D + k] * gfin[k];
   }
-  size_t o_decln = bb.add_copy(wf.get(dd + "norm.weight", {D}).data, D);
+  size_t o_decln = o_ones;
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
   size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
   struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2; };
@@ -162,9 +169,10 @@ void Model::build_weights(const WeightFile& wf) {
     const float* f1 = wf.get(p + "mlp.fc1.weight", {2 * I, D}).data;
     const float* f1b = wf.get(p + "mlp.fc1.bias", {2 * I}).data;
     const float* f2 = wf.get(p + "mlp.fc2.weight", {D, I}).data;
-    dof[l].ln1 = bb.add_copy(wf.get(p + "input_layernorm.weight", {D}).data, D);
-    dof[l].ln2 = bb.add_copy(wf.get(p + "post_attention_layernorm.weight", {D}).data, D);
-    dof[l].ln3 = bb.add_copy(wf.get(p + "final_layernorm.weight", {D}).data, D);
+    const float* g1 = wf.get(p + "input_layernorm.weight", {D}).data;
+    const float* g2 = wf.get(p + "post_attention_layernorm.weight", {D}).data;
+    const float* g3 = wf.get(p + "final_layernorm.weight", {D}).data;
+    dof[l].ln1 = dof[l].ln2 = dof[l].ln3 = o_ones;
     dof[l].b2 = bb.add_copy(wf.get(p + "mlp.fc2.bias", {D}).data, D);
     // per-head k-major blocks
     dof[l].wqkv = bb.add((size_t)H * D * 3 * hd);
@@ -177,10 +185,10 @@ void Model::build_weights(const WeightFile& wf) {
       for (int kk = 0; kk < D; kk++)
         for (int n = 0; n < hd; n++) {
           const size_t src = (size_t)(h * hd + n) * D + kk;
-          wqkv[(size_t)kk * 3 * hd + n] = q[src];
-          wqkv[(size_t)kk * 3 * hd + hd + n] = k[src];
-          wqkv[(size_t)kk * 3 * hd + 2 * hd + n] = v[src];
-          wqc[(size_t)kk * hd + n] = qc[src];
+          wqkv[(size_t)kk * 3 * hd + n] = q[src] * g1[kk];
+          wqkv[(size_t)kk * 3 * hd + hd + n] = k[src] * g1[kk];
+          wqkv[(size_t)kk * 3 * hd + 2 * hd + n] = v[src] * g1[kk];
+          wqc[(size_t)kk * hd + n] = qc[src] * g2[kk];
         }
       float* wo = &bb.data[dof[l].wo + (size_t)h * hd * D];
       float* woc = &bb.data[dof[l].woc + (size_t)h * hd * D];
@@ -202,8 +210,8 @@ void Model::build_weights(const WeightFile& wf) {
         b1[n] = f1b[c * IC + n];
         b1[IC + n] = f1b[I + c * IC + n];
         for (int kk = 0; kk < D; kk++) {
-          w1[(size_t)kk * 2 * IC + n] = f1[(size_t)(c * IC + n) * D + kk];
-          w1[(size_t)kk * 2 * IC + IC + n] = f1[(size_t)(I + c * IC + n) * D + kk];
+          w1[(size_t)kk * 2 * IC + n] = f1[(size_t)(c * IC + n) * D + kk] * g3[kk];
+          w1[(size_t)kk * 2 * IC + IC + n] = f1[(size_t)(I + c * IC + n) * D + kk] * g3[kk];
         }
       }
       for (int kk = 0; kk < IC; kk++)
@@ -232,7 +240,7 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
-  dec_.embS = base + o_embS; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
+  dec_.embS = base + o_embS; dec_.vcp = vcp; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   for (int l = 0; l < d_.dec_layers; l++) {
     DecLayerWeights& w = dec_.layers[l];
     w.ln1 = base + dof[l].ln1; w.wqkv = base + dof[l].wqkv; w.wo = base + dof[l].wo;
@@ -595,7 +603,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   const int grid = sm_count_;
   // v2 streams operands through the smem ring; its cross-attention maps one thread to 4 key
   // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
-  const bool use_v2 = decoder_v2_ && Tpad <= 1024;
+  const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 16 == 0;
   static const int prof_step = std::getenv("MOONSHINE_B200_PROF") ? std::atoi(std::getenv("MOONSHINE_B200_PROF")) : -1;
   DeviceBuffer<unsigned long long> prof_buf;
   if (prof_step >= 0) {

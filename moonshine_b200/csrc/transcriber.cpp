@@ -71,6 +71,7 @@ void Segmenter::start() {
   segments_.clear();
   current_.clear();
   look_behind_.assign(look_behind_count_, 0.f);
+  look_behind_pos_ = 0;
   remainder_.clear();
   probability_window_.assign(window_size_, 0.f);
   probability_index_ = 0;
@@ -112,11 +113,16 @@ void Segmenter::sync_open_segment_audio() {
 
 void Segmenter::process_hop(const float* hop) {
   samples_processed_ += hop_size_;
-  if (look_behind_.size() >= (size_t)hop_size_) {
-    std::move(look_behind_.begin() + hop_size_, look_behind_.end(), look_behind_.begin());
-    std::copy(hop, hop + hop_size_, look_behind_.end() - hop_size_);
-  } else if (!look_behind_.empty()) {
-    std::copy(hop + hop_size_ - look_behind_.size(), hop + hop_size_, look_behind_.begin());
+  // look-behind as a ring (the reference shifts the whole 8192-sample buffer on every hop;
+  // the content a voice start sees is identical)
+  if (!look_behind_.empty()) {
+    const size_t n = look_behind_.size();
+    const size_t take = std::min(n, (size_t)hop_size_);
+    const float* src = hop + hop_size_ - take;
+    for (size_t i = 0; i < take; i++) {
+      look_behind_[look_behind_pos_] = src[i];
+      look_behind_pos_ = (look_behind_pos_ + 1) % n;
+    }
   }
   float smoothed;
   if (threshold_ > 0.0f) {
@@ -134,9 +140,11 @@ void Segmenter::process_hop(const float* hop) {
   }
   const bool is_voice = smoothed > threshold_;
   if (is_voice && !previous_is_voice_) {
-    const size_t lb = std::min(look_behind_.size(), samples_processed_);
-    current_.assign(look_behind_.end() - lb, look_behind_.end());
-    if (look_behind_.size() < (size_t)hop_size_ && lb < (size_t)hop_size_) {
+    const size_t n = look_behind_.size();
+    const size_t lb = std::min(n, samples_processed_);
+    current_.resize(lb);
+    for (size_t i = 0; i < lb; i++) current_[i] = look_behind_[(look_behind_pos_ + n - lb + i) % n];
+    if (n < (size_t)hop_size_ && lb < (size_t)hop_size_) {
       // look-behind shorter than a hop: the hop itself still starts the segment
       current_.assign(hop, hop + hop_size_);
     }
@@ -145,7 +153,8 @@ void Segmenter::process_hop(const float* hop) {
     current_.insert(current_.end(), hop, hop + hop_size_);
     on_voice_end();
     current_.clear();
-    look_behind_.assign(look_behind_count_, 0.f);
+    // (the reference's `look_behind.resize(count, 0.0f)` here is a no-op on an already
+    // full-size vector, so the look-behind keeps its audio across the cut)
   } else if (is_voice && previous_is_voice_) {
     current_.insert(current_.end(), hop, hop + hop_size_);
     on_voice_continuing();

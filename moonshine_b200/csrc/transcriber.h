@@ -72,6 +72,7 @@ class Segmenter {
   size_t samples_processed_ = 0;
   std::vector<float> probability_window_;
   size_t probability_index_ = 0;
+  size_t look_behind_pos_ = 0;  // ring write position of look_behind_
   std::vector<float> look_behind_, current_, remainder_;
   std::vector<Segment> segments_;
 };

@@ -116,6 +116,26 @@ def test_skip_transcription_default_vad_splits_long_audio(lib):
     t.close()
 
 
+def test_default_vad_look_behind_content(lib):
+    """Default threshold (0.5): the 16-hop smoothing window opens the first segment at hop 9
+    and the 8192-sample look-behind reaches back to sample 0; a later segment starts with the
+    look-behind taken across the cut (voice-activity-detector.cpp:171-190)."""
+    t = api.Transcriber(None, api.ModelArch.TINY, {"skip_transcription": "true"})
+    rng = np.random.default_rng(7)
+    audio = (rng.standard_normal(16000 * 23) * 0.05).astype(np.float32)
+    tr = t.transcribe_without_streaming(audio)
+    first = tr.lines[0]
+    assert first.start_time < 1e-3
+    np.testing.assert_array_equal(first.audio_data, audio[: first.audio_data.size])
+    # every line is a contiguous slice of the input that ends on a hop boundary
+    for l in tr.lines:
+        n = l.audio_data.size
+        end = int(round((l.start_time + l.duration) * 16000))
+        assert end % 512 == 0
+        np.testing.assert_array_equal(l.audio_data, audio[end - n: end])
+    t.close()
+
+
 def test_streaming_line_invariants_without_a_device(lib):
     """core/transcriber-test.cpp:199-403 style invariants on the stream API."""
     t = api.Transcriber(None, api.ModelArch.TINY, {"skip_transcription": "true", "vad_threshold": "0"})
