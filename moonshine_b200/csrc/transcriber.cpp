@@ -6,6 +6,7 @@
 #include <cmath>
 #include <numeric>
 #include <random>
+#include <thread>
 
 namespace msb {
 
@@ -119,10 +120,10 @@ void Segmenter::process_hop(const float* hop) {
     const size_t n = look_behind_.size();
     const size_t take = std::min(n, (size_t)hop_size_);
     const float* src = hop + hop_size_ - take;
-    for (size_t i = 0; i < take; i++) {
-      look_behind_[look_behind_pos_] = src[i];
-      look_behind_pos_ = (look_behind_pos_ + 1) % n;
-    }
+    const size_t first = std::min(take, n - look_behind_pos_);
+    std::copy(src, src + first, look_behind_.begin() + look_behind_pos_);
+    std::copy(src + first, src + take, look_behind_.begin());
+    look_behind_pos_ = (look_behind_pos_ + take) % n;
   }
   float smoothed;
   if (threshold_ > 0.0f) {
@@ -143,7 +144,10 @@ void Segmenter::process_hop(const float* hop) {
     const size_t n = look_behind_.size();
     const size_t lb = std::min(n, samples_processed_);
     current_.resize(lb);
-    for (size_t i = 0; i < lb; i++) current_[i] = look_behind_[(look_behind_pos_ + n - lb + i) % n];
+    const size_t start = (look_behind_pos_ + n - lb) % n;
+    const size_t first = std::min(lb, n - start);
+    std::copy(look_behind_.begin() + start, look_behind_.begin() + start + first, current_.begin());
+    std::copy(look_behind_.begin(), look_behind_.begin() + (lb - first), current_.begin() + first);
     if (n < (size_t)hop_size_ && lb < (size_t)hop_size_) {
       // look-behind shorter than a hop: the hop itself still starts the segment
       current_.assign(hop, hop + hop_size_);
@@ -395,11 +399,32 @@ void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* le
     if (audio[i] == nullptr && lengths[i] > 0) throw std::runtime_error("Audio data is nullptr");
     batch_outputs_.push_back(std::make_unique<TranscriptOutput>());
     vads.push_back(make_segmenter());
-    vads.back()->start();
-    vads.back()->process_audio(audio[i], (size_t)lengths[i], sample_rate);
-    vads.back()->stop();
-    jobs.push_back(Job{batch_outputs_.back().get(), &vads.back()->segments(), true});
   }
+  // utterances are independent: resample + segment them on a few host threads
+  {
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, count / 2));
+    auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++) {
+        vads[i]->start();
+        vads[i]->process_audio(audio[i], (size_t)lengths[i], sample_rate);
+        vads[i]->stop();
+      }
+    };
+    if (nthreads <= 1) {
+      work(0, count);
+    } else {
+      std::vector<std::thread> pool;
+      const uint64_t per = (count + nthreads - 1) / nthreads;
+      for (unsigned t = 0; t < nthreads; t++) {
+        const uint64_t lo = t * per, hi = std::min<uint64_t>(count, lo + per);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+      }
+      for (auto& th : pool) th.join();
+    }
+  }
+  for (uint64_t i = 0; i < count; i++)
+    jobs.push_back(Job{batch_outputs_[i].get(), &vads[i]->segments(), true});
   update_outputs(jobs);
   for (uint64_t i = 0; i < count; i++) batch_transcripts_[i] = batch_outputs_[i]->transcript;
   if (out) *out = batch_transcripts_.data();

@@ -85,6 +85,14 @@ def test_small_arch2_batch_many():
     check_case("test2", 3, "scaled", audios)
 
 
+@pytest.mark.parametrize("B", [100, 130], ids=["B100_tile8", "B130_tile16"])
+def test_small_arch_large_batch_tensor_core_tiles(B):
+    """B >= 97 switches the decoder's layer GEMMs to the mma.sync row tiles (8 / 16
+    utterances per work item); ragged short clips keep the oracle fast."""
+    audios = [synth_audio(500 + i, 2500 + 137 * (i % 23) + 16 * i) for i in range(B)]
+    check_case("test", 0, "scaled", audios)
+
+
 def test_tiny_beckett_and_synth():
     check_case("tiny", 0, "scaled", [beckett(), synth_audio(0)])
 
