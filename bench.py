@@ -289,8 +289,11 @@ def main():
             "stage_ms": {"frontend": float(np.mean(fe_ms)), "encoder": float(np.mean(enc_ms)),
                          "cross_kv": float(np.mean(xkv_ms)), "decode": float(np.mean(dec_ms)),
                          "decode_launch_us": 1000.0 * launch_ms},
-            "roofline": {"kernel": "decoder_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"kernel": "decoder_step2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed
+                         # ncu --set full capture of this exact workload (profiles/r1_final_decoder_step2_*)
+                         "traffic": 194993664.0 if (model == "tiny" and B == 32) else None,
                          "bytes_per_launch": bytes_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * N_SAMPLES * 4,
