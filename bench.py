@@ -186,7 +186,7 @@ def main():
     blob = pack_msw(model, weights) if rank == 0 else b""
     msw = broadcast_bytes(blob, 0, device=f"cuda:{local}")
     del blob
-    tr = api.Transcriber(model_arch=arch_enum, options={"vad_threshold": "0", "device": str(local)},
+    tr = api.Transcriber(model_arch=arch_enum, options={"vad_threshold": "0", "device": str(local), "return_audio_data": "false"},
                          memory_files={"model.msw": msw, "tokenizer.bin": synth_tokenizer_bin(d.vocab)})
     tr.set_timing(True)
 
@@ -239,13 +239,16 @@ def main():
     for _ in range(2):
         tr.transcribe_batch_without_streaming(audios)
     sync_all()
-    w0 = time.perf_counter()
+    e2e_total = 0.0
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
+        # the call is synchronous (it returns the transcripts), so wall clock around it is end to end;
+        # the L2 flush stays outside
+        w0 = time.perf_counter()
         res = tr.transcribe_batch_without_streaming(audios)
+        e2e_total += time.perf_counter() - w0
     sync_all()
-    e2e_total = time.perf_counter() - w0
     stop_evt.set()
     th.join(timeout=3)
 
@@ -299,7 +302,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * N_SAMPLES * 4,
                     "d2h_bytes_per_step": int(sum(len(x) for x in toks) * 4 + 4 * B),
                     "ms_per_step": 1000.0 * e2e_total / K,
-                    "api": "moonshine_transcribe_batch_without_streaming (host PCM -> transcript_t)"},
+                    "api": "moonshine_transcribe_batch_without_streaming (host PCM -> transcript_t; options vad_threshold=0, return_audio_data=false)"},
             "gpu_launches": launches_per_step * K,
             "tokens_per_utt": float(np.mean(n_tokens)),
             "clocks": summarise_clocks(clock_lines, local),

@@ -23,7 +23,6 @@ namespace {
 constexpr int kConsumers = 256;
 constexpr int kThreads2 = kConsumers + 32;
 constexpr int kWarpsC = kConsumers / 32;
-constexpr int kLogitsTile = 32;
 constexpr int kStageBytes = 32768;
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s of SM cycles: trap instead of hanging
 
@@ -142,7 +141,7 @@ __device__ __forceinline__ int rows_per_chunk_f16(int rows, int cols) {
 
 struct SmemLayout2 {
   int hs, xs, act, att, red, ps, sc, flags, argv, argi, active, bars, ring, rope, bias;  // byte offsets
-  int actw, attw, total, ns, xpitch;
+  int actw, attw, total, ns, xg_bytes;
 };
 
 __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int hd, int IC, int Tpad,
@@ -160,20 +159,25 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
   int red = (NBmax <= 4 ? 1024 * NBmax : 0) * 4;
   if (red < (16 + 1024) * 4) red = (16 + 1024) * 4;
   L.red = take(red);
-  // the logits phase aliases [0, xg_bytes) with its 32 x xpitch x-tile (xpitch % 32 == 8)
-  L.xpitch = D + ((8 - (D % 32)) + 32) % 32;
-  const int xg_bytes = kLogitsTile * L.xpitch * 4;
-  if (o < xg_bytes) o = (xg_bytes + 15) / 16 * 16;
+  // the logits phase aliases [0, xg_bytes) with the bf16 hi/lo planes of its x tile
+  // (nx utterances x D x 4 bytes, nx = min(64, round_up(B, 16)) but at most ~80 KB)
+  {
+    int nx = (B + 15) & ~15;
+    if (nx > 64) nx = 64;
+    while (nx > 16 && nx * D * 4 > 80 * 1024) nx -= 16;
+    L.xg_bytes = nx * D * 4;
+    if (o < L.xg_bytes) o = (L.xg_bytes + 15) / 16 * 16;
+  }
   L.ps = take(Tpad * 4);
   L.sc = take(kWarpsC * (Smax + 4) * 4);
   L.flags = take(64 * 4);
-  L.argv = take(kWarpsC * kLogitsTile * 4);
-  L.argi = take(kWarpsC * kLogitsTile * 4);
+  L.argv = take(kWarpsC * 64 * 4);
+  L.argi = take(kWarpsC * 64 * 4);
   L.rope = take(128 * 4);
   L.bias = take(2 * IC * 4);
   L.active = take(B);
-  L.bars = take(2 * 16 * 8);
-  o = (o + 127) / 128 * 128;
+  L.bars = take((2 * 16 + 2) * 8);  // ring full/empty, accumulator barrier, TMEM base
+  o = (o + 1023) / 1024 * 1024;  // SWIZZLE_64B operand chunks need 512-byte aligned stages
   L.ring = o;
   int ns = (smem_limit - o) / kStageBytes;
   if (ns > 16) ns = 16;
@@ -186,8 +190,11 @@ constexpr int kProfSlots = 512;
 struct Ctx {
   const float* rope;         // smem: cos[0..64) | sin[64..128) of this step's position
   float* bias;               // smem: staged FC1 bias chunk (2 * IC floats)
-  float* xg;                 // smem: [32][xpitch] final-LN rows for the logits phase (aliases hs..red)
-  int xpitch;
+  float* xg;                 // smem: bf16 hi/lo planes of the logits x tile (aliases hs..red)
+  int nx;                    // utterances per logits pass (multiple of 16, <= 64)
+  uint32_t tmem;             // TMEM base (128 columns)
+  uint64_t* acc_bar;         // accumulator-ready mbarrier
+  int acc_phase;
   unsigned long long* prof;  // optional [grid][kProfSlots] globaltimer stamps (thread 0)
   int prof_n;
   float *hs, *xs, *act, *att, *red, *ps, *sc, *argv;
@@ -842,147 +849,205 @@ __device__ void phase_final_ln(const DecoderParams& p, int item, Ctx& c, const f
 }
 
 // ============================== phase G =================================
-// Tied-embedding logits on the tensor cores (mma.sync m16n8k16, bf16x3 split, fp32
-// accumulate): per pass a [32 utterances x D] tile of final-LN rows times the CTA's
-// vocab slab embS[item] = [D][VCP] (k-major, row pitch VCP = vchunk + 4 keeps the
-// B-fragment loads bank-conflict free), streamed through the ring 16 rows (one k-step)
-// at a time.  The per-utterance argmax is fused: no logits leave the SM.
-__device__ __forceinline__ int slab_rows_per_chunk(int vcp) {
-  int r = (kStageBytes / (vcp * 4)) & ~15;
-  return r < 16 ? 16 : r;
+// Tied-embedding logits on tcgen05.  The CTA's vocab slab arrives through the ring ALREADY in the
+// tensor core's operand format (bf16 hi/lo planes, K-major SWIZZLE_64B, built once at load time),
+// so the only consumer of those stages is the MMA itself: thread 0 issues
+//   D[128 vocab rows][Nx utterances] += A(slab chunk) * B(x planes)^T      (kind::f16, bf16x3)
+// into TMEM and tcgen05.commit releases the ring stage when the MMAs have read it.  The x tile
+// (final-LN rows of up to 64 utterances) is split to bf16 planes in shared memory once per pass.
+// Epilogue: tcgen05.ld gives each thread one vocab row x Nx utterances; the per-utterance argmax is
+// reduced across the CTA and only (value, index) candidates leave the SM.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;    // SBO: 8 rows * 64 B
+  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;             // SWIZZLE_64B
+  return d;
 }
-__device__ __forceinline__ void produce_logits(const DecoderParams& p, int item, Ring& ring) {
-  const float* slab = p.embS + (int64_t)item * p.D * p.vcp;
-  const int rpc = slab_rows_per_chunk(p.vcp);
-  for (int b0 = 0; b0 < p.B; b0 += kLogitsTile)
-    for (int k0 = 0; k0 < p.D; k0 += rpc) {
-      const int rows = min(rpc, p.D - k0);
-      ring.produce(slab + (size_t)k0 * p.vcp, (uint32_t)rows * p.vcp * 4);
-    }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// (a, b) -> packed bf16 pairs: hi = round-to-nearest bf16, lo = bf16 of the remainder (a in the low half)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+  const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+__device__ __forceinline__ int logits_rows_per_pass(int B, int D, int xg_bytes) {
+  int nx = (xg_bytes / (D * 4)) & ~15;
+  if (nx > 64) nx = 64;
+  const int b16 = (B + 15) & ~15;
+  return nx < b16 ? nx : b16;
 }
 
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+// chunk = up to two 32-wide k-blocks of one m-tile: [kb][hi R x 64 B | lo R x 64 B]
+__device__ __forceinline__ void produce_logits(const DecoderParams& p, int item, Ring& ring, int nx) {
+  const int D = p.D, VC = p.vchunk;
+  const int n_mt = (VC + 127) >> 7, nkb = D >> 5;
+  const unsigned char* slab = reinterpret_cast<const unsigned char*>(p.embP) + (size_t)item * VC * D * 4;
+  for (int b0 = 0; b0 < p.B; b0 += nx) {
+    size_t mt_off = 0;
+    for (int mt = 0; mt < n_mt; mt++) {
+      const int R = min(128, VC - mt * 128);
+      for (int kb = 0; kb < nkb; kb += 2) {
+        const int n = min(2, nkb - kb);
+        ring.produce(slab + mt_off + (size_t)kb * R * 128, (uint32_t)(n * R * 128));
+      }
+      mt_off += (size_t)R * D * 4;
+    }
+  }
 }
 
 __device__ void phase_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring) {
-  const int D = p.D, V = p.V, VC = p.vchunk, VCP = p.vcp;
+  const int D = p.D, V = p.V, VC = p.vchunk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int XP = c.xpitch;
-  float* xg = c.xg;                     // [32][XP] fp32 rows of the final LN
-  const int NT = VC >> 3;               // n-tiles of 8 vocab entries (<= 32)
+  const int n_mt = (VC + 127) >> 7, nkb = D >> 5;
+  const int nx = c.nx;
   const int parity = p.step & 1;
-  const int rpc = slab_rows_per_chunk(VCP);
-  for (int b0 = 0; b0 < p.B; b0 += kLogitsTile) {
-    const int nb = min(kLogitsTile, p.B - b0);
-    for (int i = threadIdx.x; i < kLogitsTile * D; i += kConsumers) {
-      const int b = i / D, k = i - b * D;
-      xg[b * XP + k] = (b < nb) ? p.xfin[(int64_t)(b0 + b) * D + k] : 0.f;
-    }
-    csync();
-    float acc[2][4][4];
+  unsigned char* xp = reinterpret_cast<unsigned char*>(c.xg);  // [kb][hi nx x 64 B | lo nx x 64 B]
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nx >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  for (int b0 = 0; b0 < p.B; b0 += nx) {
+    const int nb = min(nx, p.B - b0);
+    // ---- x planes: thread handles (row, 16-byte chunk of 8 k); loads batched 4 deep ----
+    const int k8n = D >> 3, nitems = nx * k8n;
+    for (int i0 = threadIdx.x; i0 < nitems; i0 += 4 * kConsumers) {
+      float4 va[4], vb[4];
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
-    for (int k0 = 0; k0 < D; k0 += rpc) {
-      const int rows = min(rpc, D - k0);
-      const float* W = reinterpret_cast<const float*>(ring.acquire());
-      for (int kk = 0; kk < rows; kk += 16) {   // D % 16 == 0
-        uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-          const float* xr0 = xg + (mt * 16 + g) * XP + k0 + kk + 2 * t;
-          const float* xr1 = xr0 + 8 * XP;
-          const float2 v0 = *reinterpret_cast<const float2*>(xr0);
-          const float2 v1 = *reinterpret_cast<const float2*>(xr1);
-          const float2 v2 = *reinterpret_cast<const float2*>(xr0 + 8);
-          const float2 v3 = *reinterpret_cast<const float2*>(xr1 + 8);
-          split_bf16x2(v0.x, v0.y, ahi[mt][0], alo[mt][0]);
-          split_bf16x2(v1.x, v1.y, ahi[mt][1], alo[mt][1]);
-          split_bf16x2(v2.x, v2.y, ahi[mt][2], alo[mt][2]);
-          split_bf16x2(v3.x, v3.y, ahi[mt][3], alo[mt][3]);
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * kConsumers;
+        const int r = i / k8n, k8 = i - r * k8n;
+        va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[u] = va[u];
+        if (i < nitems && r < nb) {
+          va[u] = *reinterpret_cast<const float4*>(p.xfin + (int64_t)(b0 + r) * D + k8 * 8);
+          vb[u] = *reinterpret_cast<const float4*>(p.xfin + (int64_t)(b0 + r) * D + k8 * 8 + 4);
         }
-        uint32_t bhi[4][2], blo[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int nt = warp + j * kWarpsC;
-          if (nt < NT) {  // warp-uniform
-            const float* wr = W + (kk + 2 * t) * VCP + nt * 8 + g;
-            split_bf16x2(wr[0], wr[VCP], bhi[j][0], blo[j][0]);
-            split_bf16x2(wr[8 * VCP], wr[9 * VCP], bhi[j][1], blo[j][1]);
-          }
-        }
-        // three split products; within each pass the 8 accumulators are independent
-#pragma unroll
-        for (int pass = 0; pass < 3; pass++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (warp + j * kWarpsC < NT) {
-#pragma unroll
-              for (int mt = 0; mt < 2; mt++) {
-                if (pass == 0) mma_bf16(acc[mt][j], alo[mt], bhi[j]);
-                else if (pass == 1) mma_bf16(acc[mt][j], ahi[mt], blo[j]);
-                else mma_bf16(acc[mt][j], ahi[mt], bhi[j]);
-              }
-            }
-          }
       }
-      ring.release();
-    }
-    // accumulator (mt, j): rows mt*16+g (c0,c1) and +8 (c2,c3), vocab item*VC + nt*8 + 2t (+1)
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-#pragma unroll
-      for (int hrow = 0; hrow < 2; hrow++) {
-        const int row = mt * 16 + g + hrow * 8;
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int nt = warp + j * kWarpsC;
-          if (nt < NT) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int v = item * VC + nt * 8 + 2 * t + e;
-              const float x = acc[mt][j][hrow * 2 + e];
-              if (v < V) {
-                if (p.logits_out && row < nb) p.logits_out[(int64_t)(b0 + row) * V + v] = x;
-                if (x > bv || (x == bv && v < bi)) { bv = x; bi = v; }  // NaN never wins
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {  // the 4 lanes of a group share the row
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (t == 0) { c.argv[warp * kLogitsTile + row] = bv; c.argi[warp * kLogitsTile + row] = bi; }
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * kConsumers;
+        if (i >= nitems) break;
+        const int r = i / k8n, k8 = i - r * k8n;
+        uint4 hi, lo;
+        split_bf16x2(va[u].x, va[u].y, hi.x, lo.x);
+        split_bf16x2(va[u].z, va[u].w, hi.y, lo.y);
+        split_bf16x2(vb[u].x, vb[u].y, hi.z, lo.z);
+        split_bf16x2(vb[u].z, vb[u].w, hi.w, lo.w);
+        const int kb = k8 >> 2, cc = k8 & 3;
+        unsigned char* base = xp + (size_t)kb * nx * 128 + (size_t)r * 64 + ((cc ^ ((r >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(base) = hi;
+        *reinterpret_cast<uint4*>(base + nx * 64) = lo;
       }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     csync();
+    prof_mark(c, 35);
+    // ---- MMA issue (one thread); everyone else just advances its ring cursor ----
+    int nchunks = 0;
+    for (int mt = 0; mt < n_mt; mt++) nchunks += (nkb + 1) >> 1;
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int mt = 0; mt < n_mt; mt++) {
+        const int R = min(128, VC - mt * 128);
+        const uint32_t tmem_d = c.tmem + (uint32_t)(mt * nx);
+        for (int kb = 0; kb < nkb; kb += 2) {
+          const int n = min(2, nkb - kb);
+          mbar_wait(&ring.full[ring.stage()], ring.parity());
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_u32(ring.data + (size_t)ring.stage() * kStageBytes);
+          for (int q = 0; q < n; q++) {
+            const uint32_t a_hi = a_base + (uint32_t)(q * R * 128), a_lo = a_hi + (uint32_t)(R * 64);
+            const uint32_t b_hi = smem_u32(xp + (size_t)(kb + q) * nx * 128), b_lo = b_hi + (uint32_t)(nx * 64);
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) {
+              const uint32_t ko = (uint32_t)jj * 32u;
+              const uint32_t first = (kb | q | jj) ? 1u : 0u;
+              umma_bf16(tmem_d, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, first);
+              umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_lo + ko), idesc, 1u);
+              umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, 1u);
+            }
+          }
+          // the stage is free once these MMAs have read it: the empty barrier counts kWarpsC
+          // arrivals -- (kWarpsC - 1) bookkeeping arrivals now, the real one from the commit
+          for (int a = 0; a < kWarpsC - 1; a++) mbar_arrive(&ring.empty[ring.stage()]);
+          umma_commit(&ring.empty[ring.stage()]);
+          ring.idx++;
+        }
+      }
+      umma_commit(c.acc_bar);
+      prof_mark(c, 36);
+    } else {
+      ring.idx += nchunks;
+    }
+    // ---- epilogue: TMEM -> registers, logits dump (optional), per-utterance argmax ----
+    mbar_wait(c.acc_bar, (uint32_t)(c.acc_phase & 1));
+    c.acc_phase++;
+    __syncwarp();
+    prof_mark(c, 37);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int mt_w = warp >> 2;                      // warps 0-3: m-tile 0, warps 4-7: m-tile 1
+    const int vrow = mt_w * 128 + (warp & 3) * 32 + lane;
+    const int v = item * VC + vrow;
+    const bool vok = (mt_w < n_mt) && (vrow < VC) && (v < V);
+    for (int cb = 0; cb < nx; cb += 16) {
+      uint32_t r[16];
+      if (mt_w < n_mt) {  // warp-uniform
+        const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt_w * nx + cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const int b = cb + e;
+        const float val = __uint_as_float(r[e]);
+        if (vok && p.logits_out && b < nb) p.logits_out[(int64_t)(b0 + b) * V + v] = val;
+        // order-preserving float -> uint key (NaN and masked rows -> 0, never win); one redux gives the
+        // warp max, the lowest lane holding it is the first (smallest) vocab index
+        uint32_t key = r[e];
+        key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+        if (!vok || val != val) key = 0u;
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+        const uint32_t who = __ballot_sync(0xffffffffu, key == mx);
+        if (lane == 0) {
+          c.argv[warp * 64 + b] = __uint_as_float(mx);
+          c.argi[warp * 64 + b] = mx ? item * VC + mt_w * 128 + (warp & 3) * 32 + (__ffs(who) - 1) : 0x7fffffff;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    csync();
+    prof_mark(c, 38);
     if (threadIdx.x < nb) {
       const int b = threadIdx.x;
-      float bv = -INFINITY;
+      uint32_t bk = 0u;
       int bi = 0x7fffffff;
       for (int w2 = 0; w2 < kWarpsC; w2++) {
-        const float ov = c.argv[w2 * kLogitsTile + b];
-        const int oi = c.argi[w2 * kLogitsTile + b];
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        const uint32_t ok = __float_as_uint(c.argv[w2 * 64 + b]);
+        const int oi = c.argi[w2 * 64 + b];
+        if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
       }
+      // key -> float (0 = no candidate)
+      const float bv = bk == 0u ? -INFINITY : __uint_as_float((bk & 0x80000000u) ? (bk & 0x7fffffffu) : ~bk);
       p.cand_val[((int64_t)parity * p.n_vchunk + item) * p.B + b0 + b] = bv;
       p.cand_idx[((int64_t)parity * p.n_vchunk + item) * p.B + b0 + b] = bi;
     }
@@ -994,7 +1059,7 @@ template <int NB, int NBM>
 __global__ void __launch_bounds__(kThreads2, 1)
 decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   if (*p.n_active == 0) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int NBmax = NB > NBM ? NB : NBM;
   const SmemLayout2 L = smem_layout2(NBmax, p.B, p.D, p.hd, p.IC, p.Tpad, p.Smax, p.smem_limit);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
@@ -1008,14 +1073,25 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
 
   // snapshot of the done flags: the work list of this launch
   for (int b = threadIdx.x; b < p.B; b += kThreads2) active[b] = p.done[b] ? 0 : 1;
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 33);
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.ns; i++) {
       mbar_init(&ring.full[i], 1);
       mbar_init(&ring.empty[i], kWarpsC);
     }
+    mbar_init(bars + 32, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 32) {  // warp 0 owns the TMEM allocation (128 columns: 2 m-tiles x <= 64 utterances)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
 
   const unsigned G = gridDim.x;
   const int n_bt = (p.B + NB - 1) / NB;
@@ -1029,7 +1105,8 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
         for (int it = blockIdx.x; it < n_bt * p.H; it += G) produce_cross(p, l, it, NB, ring, active);
         for (int it = blockIdx.x; it < n_btm * p.n_chunk; it += G) produce_mlp(p, l, it, NBM, ring, active);
       }
-      for (int it = blockIdx.x; it < p.n_vchunk; it += G) produce_logits(p, it, ring);
+      const int nx = logits_rows_per_pass(p.B, p.D, L.xg_bytes);
+      for (int it = blockIdx.x; it < p.n_vchunk; it += G) produce_logits(p, it, ring, nx);
     }
     return;
   }
@@ -1059,7 +1136,10 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
     c.rope = rope;
     c.bias = reinterpret_cast<float*>(smem_raw + L.bias);
     c.xg = reinterpret_cast<float*>(smem_raw);
-    c.xpitch = L.xpitch;
+    c.nx = logits_rows_per_pass(p.B, p.D, L.xg_bytes);
+    c.tmem = tmem_base;
+    c.acc_bar = bars + 32;
+    c.acc_phase = 0;
   }
   c.prof = reinterpret_cast<unsigned long long*>(p.prof);
   c.prof_n = 0;
@@ -1126,6 +1206,12 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
       *p.n_active = *cnt;
       p.barrier[1] = nbar;
     }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  csync();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
   }
 }
 

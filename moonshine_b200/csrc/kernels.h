@@ -112,8 +112,8 @@ struct DecoderParams {
   DecLayerWeights layers[kMaxDecLayers];
   const float* embed;     // [V][D]   (gather)
   const float* embT;      // [D][V]   (tied logits head, k-major)
-  const float* embS;      // [n_vchunk][D][vcp] per-chunk slabs of embT, row pitch vcp = vchunk + 4 (v2 kernel)
-  int vcp;
+  const void* embP;       // v2 logits slab: bf16 hi/lo planes in UMMA K-major SWIZZLE_64B order,
+                          // [n_vchunk][m-tile][k-block of 32][plane][rows][32] (see Model::build_weights)
   int smem_limit;         // opt-in shared memory per CTA (v2 ring sizing)
   void* prof;             // optional [grid][512] u64 timestamps (v2 kernel, debugging)
   const float* final_ln;  // [D]

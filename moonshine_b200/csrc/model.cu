@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 namespace msb {
 
@@ -143,13 +145,49 @@ void Model::build_weights(const WeightFile& wf) {
   size_t o_embT = bb.add((size_t)D * V);
   for (int v = 0; v < V; v++)
     for (int k = 0; k < D; k++) bb.data[o_embT + (size_t)k * V + v] = emb[(size_t)v * D + k] * gfin[k];
-  // per-vocab-chunk slabs [n_vchunk][D][vchunk] (zero padded) for the streamed logits phase
-  const int vcp = vchunk_ + 4;
-  size_t o_embS = bb.add((size_t)n_vchunk_ * D * vcp);
-  for (int v = 0; v < V; v++) {
-    const int ch = v / vchunk_, j = v % vchunk_;
-    for (int k = 0; k < D; k++)
-      bb.data[o_embS + ((size_t)ch * D + k) * vcp + j] = emb[(size_t)v * D + k] * gfin[k];
+  // Logits slab for the tcgen05 logits phase: (embedding * final-LN gamma) split into bf16 hi/lo
+  // planes, laid out exactly as the UMMA K-major SWIZZLE_64B shared-memory tiles the kernel issues
+  // MMAs on: [vocab chunk][m-tile of <=128 rows][k-block of 32][plane hi|lo][row][32 bf16], the 16-byte
+  // chunk c of row r stored at position c ^ ((r >> 1) & 3).  A ring stage receives it by one bulk copy.
+  if (D % 32 != 0 && decoder_v2_) decoder_v2_ = false;  // v2 needs whole 32-wide k-blocks
+  const int n_mt = (vchunk_ + 127) / 128;
+  const size_t slab_halfs = (size_t)n_vchunk_ * vchunk_ * D * 2;  // hi + lo
+  size_t o_embP = bb.add((slab_halfs + 1) / 2);
+  if (decoder_v2_) {
+    uint16_t* P = reinterpret_cast<uint16_t*>(&bb.data[o_embP]);
+    auto bf16_rn = [](float x) -> uint16_t {
+      uint32_t u; std::memcpy(&u, &x, 4);
+      if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+      u += 0x7fffu + ((u >> 16) & 1u);
+      return (uint16_t)(u >> 16);
+    };
+    auto bf16_to_f = [](uint16_t h) -> float { uint32_t u = (uint32_t)h << 16; float f; std::memcpy(&f, &u, 4); return f; };
+    const int nkb = D / 32;
+    for (int ch = 0; ch < n_vchunk_; ch++) {
+      size_t chunk_base = (size_t)ch * vchunk_ * D * 2;
+      size_t mt_base = chunk_base;
+      for (int mt = 0; mt < n_mt; mt++) {
+        const int R = std::min(128, vchunk_ - mt * 128);
+        for (int kb = 0; kb < nkb; kb++) {
+          uint16_t* hi = P + mt_base + (size_t)kb * 2 * R * 32;
+          uint16_t* lo = hi + (size_t)R * 32;
+          for (int r = 0; r < R; r++) {
+            const int v = ch * vchunk_ + mt * 128 + r;
+            for (int kk = 0; kk < 32; kk++) {
+              const int k = kb * 32 + kk;
+              const float x = v < V ? emb[(size_t)v * D + k] * gfin[k] : 0.f;
+              const uint16_t h = bf16_rn(x);
+              const uint16_t l = bf16_rn(x - bf16_to_f(h));
+              const int c = kk >> 3, e = kk & 7;
+              const size_t off = (size_t)r * 32 + (size_t)((c ^ ((r >> 1) & 3)) * 8 + e);
+              hi[off] = h;
+              lo[off] = l;
+            }
+          }
+        }
+        mt_base += (size_t)R * D * 2;
+      }
+    }
   }
   size_t o_decln = o_ones;
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
@@ -240,7 +278,7 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
-  dec_.embS = base + o_embS; dec_.vcp = vcp; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
+  dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   for (int l = 0; l < d_.dec_layers; l++) {
     DecLayerWeights& w = dec_.layers[l];
     w.ln1 = base + dof[l].ln1; w.wqkv = base + dof[l].wqkv; w.wo = base + dof[l].wo;
@@ -282,13 +320,46 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
   const int64_t stride = (int64_t)((max_n + 3) / 4 * 4);
   pin_pcm_.reserve((size_t)B * stride);
   pcm_dev_.reserve((size_t)B * stride);
-  for (int b = 0; b < B; b++) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int b = 0; b < B; b++)
     if (pcm[b] == nullptr && n_samples[b] > 0) throw std::runtime_error("Audio data is nullptr");
-    std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+  // Stage through pinned memory and start each slice's DMA as soon as it is staged.  Large batches
+  // split the staging over a few host threads (one memcpy thread moves ~5 GB/s, PCIe 5 x16 ~50).
+  {
+    const size_t total_bytes = (size_t)B * stride * sizeof(float);
+    const int nthreads = total_bytes < ((size_t)2 << 20) ? 1 : std::min(8, B);
+    auto stage_rows = [&](int lo, int hi) {
+      for (int b = lo; b < hi; b++)
+        std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+    };
+    if (nthreads == 1) {
+      stage_rows(0, B);
+      CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr, pin_pcm_.ptr, total_bytes, cudaMemcpyHostToDevice, stream_));
+    } else {
+      // rows [lo, hi) of a slice are contiguous in both buffers: one DMA per slice, issued in order
+      // by this thread as the slices complete
+      std::vector<std::thread> pool;
+      std::vector<std::pair<int, int>> slices;
+      const int per = (B + nthreads - 1) / nthreads;
+      for (int lo = 0; lo < B; lo += per) slices.emplace_back(lo, std::min(B, lo + per));
+      for (auto& sl : slices) pool.emplace_back(stage_rows, sl.first, sl.second);
+      for (size_t i = 0; i < slices.size(); i++) {
+        pool[i].join();
+        const size_t off = (size_t)slices[i].first * stride;
+        const size_t cnt = (size_t)(slices[i].second - slices[i].first) * stride;
+        CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr + off, pin_pcm_.ptr + off, cnt * sizeof(float),
+                                   cudaMemcpyHostToDevice, stream_));
+      }
+    }
   }
-  CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr, pin_pcm_.ptr, (size_t)B * stride * sizeof(float),
-                             cudaMemcpyHostToDevice, stream_));
+  const auto t1 = std::chrono::steady_clock::now();
   run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg);
+  if (std::getenv("MOONSHINE_B200_HOST_PROF")) {
+    const auto t2 = std::chrono::steady_clock::now();
+    MSB_LOGF("host profile: staging memcpy %.2f ms, h2d+run %.2f ms",
+             std::chrono::duration<double, std::milli>(t1 - t0).count(),
+             std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
 }
 
 void Model::transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
@@ -603,7 +674,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   const int grid = sm_count_;
   // v2 streams operands through the smem ring; its cross-attention maps one thread to 4 key
   // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
-  const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 16 == 0;
+  const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 32 == 0;
   static const int prof_step = std::getenv("MOONSHINE_B200_PROF") ? std::atoi(std::getenv("MOONSHINE_B200_PROF")) : -1;
   DeviceBuffer<unsigned long long> prof_buf;
   if (prof_step >= 0) {

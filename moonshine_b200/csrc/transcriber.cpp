@@ -84,23 +84,35 @@ void Segmenter::stop() {
   if (previous_is_voice_) on_voice_end();
 }
 
-void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate) {
+void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate, bool last_call) {
   if (!active_) return;
   for (Segment& s : segments_) s.just_updated = false;
-  std::vector<float> buf = remainder_;
-  if (sample_rate == kSampleRate) {
-    buf.insert(buf.end(), audio, audio + n);
-  } else {
-    std::vector<float> r = resample_audio(audio, n, (float)sample_rate, (float)kSampleRate);
-    buf.insert(buf.end(), r.begin(), r.end());
+  std::vector<float> resampled;
+  if (sample_rate != kSampleRate) {
+    resampled = resample_audio(audio, n, (float)sample_rate, (float)kSampleRate);
+    audio = resampled.data();
+    n = resampled.size();
   }
+  // hops are analysed where they lie; only a hop that straddles two calls is assembled
   size_t pos = 0;
-  while (buf.size() - pos >= (size_t)hop_size_) {
-    process_hop(buf.data() + pos);
+  if (!remainder_.empty()) {
+    const size_t need = (size_t)hop_size_ - remainder_.size();
+    if (n < need) {
+      remainder_.insert(remainder_.end(), audio, audio + n);
+      pos = n;
+    } else {
+      remainder_.insert(remainder_.end(), audio, audio + need);
+      pos = need;
+      process_hop(remainder_.data());
+      remainder_.clear();
+    }
+  }
+  while (n - pos >= (size_t)hop_size_) {
+    process_hop(audio + pos);
     pos += hop_size_;
   }
-  remainder_.assign(buf.begin() + pos, buf.end());
-  sync_open_segment_audio();
+  if (pos < n) remainder_.insert(remainder_.end(), audio + pos, audio + n);
+  if (!last_call) sync_open_segment_audio();
 }
 
 // The reference copies the growing segment buffer into the segment on every
@@ -108,7 +120,7 @@ void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate)
 // returns, so the still-open segment is materialised once here.
 void Segmenter::sync_open_segment_audio() {
   if (previous_is_voice_ && !segments_.empty() && !segments_.back().is_complete) {
-    segments_.back().audio = current_;
+    segments_.back().audio = std::make_shared<const std::vector<float>>(current_);
   }
 }
 
@@ -183,7 +195,8 @@ void Segmenter::on_voice_continuing() {
 }
 void Segmenter::on_voice_end() {
   Segment& s = segments_.back();
-  s.audio = current_;
+  s.audio = std::make_shared<const std::vector<float>>(std::move(current_));  // every caller clears current_ next
+  current_.clear();
   s.end_time = seconds_from_samples(samples_processed_);
   s.is_complete = true;
   s.just_updated = true;
@@ -219,7 +232,7 @@ void TranscriptOutput::add_or_update(Line& line) {
     line.is_new = 1;
     line.has_text_changed = line.has_text ? 1 : 0;
   }
-  lines[line.id] = line;
+  lines[line.id] = std::move(line);
 }
 void TranscriptOutput::mark_all_complete() {
   for (uint64_t id : order) {
@@ -238,8 +251,8 @@ void TranscriptOutput::rebuild() {
     const Line& l = lines[id];
     transcript_line_t c{};
     c.text = l.has_text ? l.text.c_str() : nullptr;
-    c.audio_data = l.audio.empty() ? nullptr : l.audio.data();
-    c.audio_data_count = l.audio.size();
+    c.audio_data = (l.audio && !l.audio->empty()) ? l.audio->data() : nullptr;
+    c.audio_data_count = l.audio ? l.audio->size() : 0;
     c.start_time = l.start_time;
     c.duration = l.duration;
     c.id = l.id;
@@ -349,8 +362,8 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
           p.line.has_text = true;  // empty string, like the reference
         } else {
           p.run = true;
-          ptrs.push_back(s.audio.data());
-          lens.push_back(s.audio.size());
+          ptrs.push_back(s.data());
+          lens.push_back(s.size());
         }
       }
       pend.push_back(std::move(p));
@@ -364,6 +377,9 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens);
     latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                      std::chrono::steady_clock::now() - t0).count();
+    if (std::getenv("MOONSHINE_B200_HOST_PROF"))
+      MSB_LOGF("host profile: model.transcribe %.2f ms for %zu segments",
+               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ptrs.size());
   }
   size_t ti = 0;
   for (Pending& p : pend) {
@@ -389,6 +405,8 @@ void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* le
                                    transcript_t** out) {
   (void)flags;
   std::lock_guard<std::mutex> lock(batch_mutex_);
+  static const bool host_prof = std::getenv("MOONSHINE_B200_HOST_PROF") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
   // every call starts from fresh line state, like stream->start() does for
   // the reference's batch stream (transcriber.cpp:679-683)
   batch_outputs_.clear();
@@ -407,7 +425,7 @@ void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* le
     auto work = [&](uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; i++) {
         vads[i]->start();
-        vads[i]->process_audio(audio[i], (size_t)lengths[i], sample_rate);
+        vads[i]->process_audio(audio[i], (size_t)lengths[i], sample_rate, /*last_call=*/true);
         vads[i]->stop();
       }
     };
@@ -423,11 +441,17 @@ void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* le
       for (auto& th : pool) th.join();
     }
   }
+  const auto tp1 = std::chrono::steady_clock::now();
   for (uint64_t i = 0; i < count; i++)
     jobs.push_back(Job{batch_outputs_[i].get(), &vads[i]->segments(), true});
   update_outputs(jobs);
   for (uint64_t i = 0; i < count; i++) batch_transcripts_[i] = batch_outputs_[i]->transcript;
   if (out) *out = batch_transcripts_.data();
+  if (host_prof) {
+    const auto tp2 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    MSB_LOGF("host profile: segment %.2f ms, model+text %.2f ms", ms(tp0, tp1), ms(tp1, tp2));
+  }
 }
 
 void Transcriber::transcribe_without_streaming(const float* audio, uint64_t n, int32_t sample_rate,
@@ -511,7 +535,7 @@ void Transcriber::transcribe_stream(int32_t id, uint32_t flags, transcript_t** o
   update_outputs(jobs);
   if (!options_.return_audio_data) {
     for (Segment& seg : s->vad->segments())
-      if (seg.is_complete) std::vector<float>().swap(seg.audio);
+      if (seg.is_complete) seg.audio.reset();
   }
   if (out) *out = &s->output.transcript;
 }

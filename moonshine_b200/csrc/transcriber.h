@@ -37,8 +37,14 @@ struct TranscriberOptions {
   int device = -1;  // additive option "device": CUDA ordinal (-1 = current / LOCAL_RANK)
 };
 
+// Segment audio is immutable once published: the segmenter replaces the buffer instead of
+// growing it in place, so transcript lines can share it without copying.
+using AudioRef = std::shared_ptr<const std::vector<float>>;
+
 struct Segment {
-  std::vector<float> audio;
+  AudioRef audio;
+  const float* data() const { return audio ? audio->data() : nullptr; }
+  size_t size() const { return audio ? audio->size() : 0; }
   float start_time = 0.f;
   float end_time = 0.f;
   bool is_complete = false;
@@ -56,7 +62,8 @@ class Segmenter {
   void start();
   void stop();
   bool is_active() const { return active_; }
-  void process_audio(const float* audio, size_t n, int32_t sample_rate);
+  // `last_call`: stop() follows immediately, so the still-open segment need not be materialised
+  void process_audio(const float* audio, size_t n, int32_t sample_rate, bool last_call = false);
   std::vector<Segment>& segments() { return segments_; }
 
  private:
@@ -80,7 +87,7 @@ class Segmenter {
 struct Line {
   bool has_text = false;
   std::string text;
-  std::vector<float> audio;
+  AudioRef audio;
   float start_time = 0.f, duration = 0.f;
   uint64_t id = 0;
   int8_t is_complete = 0, just_updated = 0, is_new = 0, has_text_changed = 0;

@@ -142,11 +142,15 @@ def test_streaming_line_invariants_without_a_device(lib):
     s = t.create_stream()
     s.start()
     rng = np.random.default_rng(1)
-    seen_complete = False
+    fed = np.zeros(0, np.float32)
     for i in range(6):
-        s.add_audio((rng.standard_normal(4000) * 0.05).astype(np.float32))
+        chunk = (rng.standard_normal(4000) * 0.05).astype(np.float32)
+        fed = np.concatenate([fed, chunk])
+        s.add_audio(chunk)
         tr = s.update_transcription(api.MOONSHINE_FLAG_FORCE_UPDATE)
         assert len(tr.lines) == 1
+        # hops that straddle two add_audio calls are assembled: the line holds every whole hop so far
+        np.testing.assert_array_equal(tr.lines[0].audio_data, fed[: fed.size // 512 * 512])
         assert not tr.lines[0].is_complete  # only the last line may be incomplete
         assert tr.lines[0].is_new == (i == 0)
     # no new audio, no force: cached transcript, flags cleared
