@@ -31,6 +31,8 @@ MSW_MAGIC = b"MSW1"
 def tensor_specs(d: ModelDims) -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, kind) in canonical order.  kind in
     {weight, bias, norm_w, norm_b, embed}; fan_in is shape[1:] product."""
+    if d.streaming:
+        return streaming_tensor_specs(d)
     D, I, V = d.dim, d.ffn, d.vocab
     specs: List[Tuple[str, Tuple[int, ...], str]] = []
     e = "model.encoder."
@@ -76,6 +78,72 @@ def tensor_specs(d: ModelDims) -> List[Tuple[str, Tuple[int, ...], str]]:
     return specs
 
 
+STREAMING_CONFIG_NAME = "streaming.config"
+
+
+def streaming_config_record(d: ModelDims) -> np.ndarray:
+    """The dimensions the reference reads from streaming_config.json
+    (core/moonshine-streaming-model.cpp:75-116) plus the encoder-side ones its graphs bake in
+    (lora/export.py:100-127 windows), as one float32 vector stored beside the tensors."""
+    w = [x for pf in d.windows for x in pf]
+    return np.asarray([1, d.enc_dim, d.dim, d.enc_layers, d.dec_layers, d.heads, d.head_dim, d.enc_ffn, d.ffn,
+                       d.vocab, d.rope_denominator, d.rot_dim, d.rope_theta, 1.0 if d.tied else 0.0,
+                       d.max_seq_len, d.max_pos_emb, d.bos, d.eos, len(d.windows)] + w, np.float32)
+
+
+def streaming_tensor_specs(d: ModelDims) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """HF ``MoonshineStreamingForConditionalGeneration`` state-dict keys
+    (transformers/models/moonshine_streaming/modeling_moonshine_streaming.py)."""
+    E, EI, D, I, V = d.enc_dim, d.enc_ffn, d.dim, d.ffn, d.vocab
+    specs: List[Tuple[str, Tuple[int, ...], str]] = [
+        (STREAMING_CONFIG_NAME, (19 + 2 * len(d.windows),), "config")]
+    e = "model.encoder."
+    specs += [
+        (e + "embedder.comp.log_k", (1,), "log_k"),
+        (e + "embedder.linear.weight", (E, 80), "weight"),
+        (e + "embedder.conv1.weight", (2 * E, E, 5), "weight"),
+        (e + "embedder.conv1.bias", (2 * E,), "bias"),
+        (e + "embedder.conv2.weight", (E, 2 * E, 5), "weight"),
+        (e + "embedder.conv2.bias", (E,), "bias"),
+    ]
+    for l in range(d.enc_layers):
+        p = f"{e}layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            specs.append((p + f"self_attn.{n}.weight", (E, E), "weight"))
+        specs += [
+            (p + "mlp.fc1.weight", (EI, E), "weight"),
+            (p + "mlp.fc1.bias", (EI,), "bias"),
+            (p + "mlp.fc2.weight", (E, EI), "weight"),
+            (p + "mlp.fc2.bias", (E,), "bias"),
+            (p + "input_layernorm.gamma", (E,), "gamma0"),
+            (p + "post_attention_layernorm.gamma", (E,), "gamma0"),
+        ]
+    specs.append((e + "final_norm.gamma", (E,), "gamma0"))
+    dd = "model.decoder."
+    specs.append((dd + "embed_tokens.weight", (V, D), "embed"))
+    specs.append((dd + "pos_emb.weight", (d.max_pos_emb, E), "weight02"))
+    if E != D:
+        specs.append((dd + "proj.weight", (D, E), "weight"))
+    for l in range(d.dec_layers):
+        p = f"{dd}layers.{l}."
+        for a in ("self_attn", "encoder_attn"):
+            for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                specs.append((p + f"{a}.{n}.weight", (D, D), "weight"))
+        specs += [
+            (p + "mlp.fc1.weight", (2 * I, D), "weight"),
+            (p + "mlp.fc1.bias", (2 * I,), "bias"),
+            (p + "mlp.fc2.weight", (D, I), "weight"),
+            (p + "mlp.fc2.bias", (D,), "bias"),
+            (p + "input_layernorm.weight", (D,), "norm_w"),
+            (p + "post_attention_layernorm.weight", (D,), "norm_w"),
+            (p + "final_layernorm.weight", (D,), "norm_w"),
+        ]
+    specs.append((dd + "norm.weight", (D,), "norm_w"))
+    if not d.tied:
+        specs.append(("proj_out.weight", (V, D), "embed"))
+    return specs
+
+
 def synth_weights(arch, seed: int = 0, init: str = "scaled") -> Dict[str, np.ndarray]:
     """Deterministic synthetic weights.
 
@@ -93,6 +161,19 @@ def synth_weights(arch, seed: int = 0, init: str = "scaled") -> Dict[str, np.nda
     out: Dict[str, np.ndarray] = {}
     for idx, (name, shape, kind) in enumerate(tensor_specs(d)):
         rng = np.random.default_rng([seed, idx])
+        if kind == "config":
+            out[name] = streaming_config_record(d)
+            continue
+        if kind == "log_k":   # HF init: log(0.75)
+            out[name] = np.asarray([np.log(0.75) + (0.0 if init == "hf" else 0.3)], np.float32)
+            continue
+        if kind == "gamma0":  # unit-offset norm: effective scale is gamma + 1, HF init 0
+            out[name] = (np.zeros(shape, np.float32) if init == "hf"
+                         else (0.1 * rng.standard_normal(shape, dtype=np.float32)))
+            continue
+        if kind == "weight02":  # position table: same scale in both inits
+            out[name] = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02 if init == "hf" else 0.1)
+            continue
         if kind in ("weight", "embed"):
             if init == "hf":
                 std = 0.02

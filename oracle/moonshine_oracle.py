@@ -263,10 +263,13 @@ class Oracle:
             up, gate = y[:, : d.ffn], y[:, d.ffn:]          # HF:84-90: value | gate
             h = h + self.linear(self.silu(gate) * up, p + "mlp.fc2.weight", p + "mlp.fc2.bias")
         h = self.layernorm(h, "model.decoder.norm.weight")
-        logits = self.mm(h, self.w["model.decoder.embed_tokens.weight"].T)  # tied head, HF:843
+        logits = self.head(h)
         if want_cross_attn:
             return logits, xattn
         return logits
+
+    def head(self, h):
+        return self.mm(h, self.w["model.decoder.embed_tokens.weight"].T)  # tied head, HF:843
 
     # ---- host loop: core/moonshine-model.cpp:347-349,370-371,380-517 ------
     @staticmethod
