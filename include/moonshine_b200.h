@@ -231,6 +231,10 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_run(
     float *enc_out, uint64_t enc_out_capacity, int32_t *enc_frames, const int32_t *forced,
     int32_t forced_stride, float *logits, int32_t logits_steps, int32_t *out_tokens,
     int32_t out_stride, int32_t *out_counts);
+/* Parity hook for the streaming architectures: when enabled, moonshine_b200_debug_run /
+   moonshine_b200_transcribe_device treat each utterance as a NON-final update of its segment
+   (the encoder's look-ahead features are held back, core/moonshine-streaming-model.cpp:624-626). */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_stream_partial(int32_t transcriber_handle, int32_t enabled);
 /* Standalone grouped-GEMM hook used by the kernel unit tests (device pointers). */
 MOONSHINE_EXPORT int32_t moonshine_b200_test_gemm(const float *dA, const float *dW, float *dC,
                                                   int32_t M, int32_t N, int32_t K, int32_t lda,

@@ -33,6 +33,8 @@ class ModelArch(IntEnum):
     # reduced-size architectures for unit tests (not in the reference)
     TEST = 100
     TEST2 = 101
+    TEST_STREAMING = 102
+    TEST_STREAMING2 = 103
 
 
 class MoonshineError(RuntimeError):
@@ -105,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "moonshine_free_grapheme_to_phonemizer", "moonshine_text_to_phonemes",
     "moonshine_transcribe_batch_without_streaming", "moonshine_b200_transcribe_device",
     "moonshine_b200_get_stream", "moonshine_b200_set_timing", "moonshine_b200_last_timings",
-    "moonshine_b200_debug_run", "moonshine_b200_test_gemm",
+    "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial", "moonshine_b200_test_gemm",
 ]
 
 _lib = None
@@ -171,6 +173,8 @@ def load_library() -> ctypes.CDLL:
     lib.moonshine_b200_set_timing.argtypes = [c.c_int32, c.c_int32]
     lib.moonshine_b200_last_timings.restype = c.c_int32
     lib.moonshine_b200_last_timings.argtypes = [c.c_int32, c.POINTER(c.c_double)]
+    lib.moonshine_b200_debug_stream_partial.restype = c.c_int32
+    lib.moonshine_b200_debug_stream_partial.argtypes = [c.c_int32, c.c_int32]
     lib.moonshine_b200_debug_run.restype = c.c_int32
     lib.moonshine_b200_debug_run.argtypes = [
         c.c_int32, c.POINTER(f32p), u64p, c.c_uint64, f32p, c.c_uint64, i32p, i32p, c.c_int32, f32p,
@@ -349,6 +353,11 @@ class Transcriber:
                 "weight_bytes"]
         return {k: out[i] for i, k in enumerate(keys)}
 
+    def debug_stream_partial(self, enabled: bool):
+        """Streaming archs: model-level calls act as a non-final update (look-ahead features held back)."""
+        _check(self._lib.moonshine_b200_debug_stream_partial(self._handle, int(bool(enabled))),
+               "debug_stream_partial failed")
+
     def debug_run(self, audios: Sequence, dim: int, vocab: int, forced: Optional[np.ndarray] = None,
                   logits_steps: int = 0, want_encoder: bool = True, max_tokens: int = 128):
         """Parity hook: returns (enc_out list per utterance, logits[steps,B,V] or None, tokens list)."""
@@ -357,7 +366,7 @@ class Transcriber:
         ptrs = (ctypes.POINTER(ctypes.c_float) * n)(*[a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for a in arrs])
         lens = (ctypes.c_uint64 * n)(*[a.size for a in arrs])
         frames = np.zeros(n, np.int32)
-        cap = sum((a.size // 384 + 2) for a in arrs) * dim
+        cap = sum((a.size // 320 + 2) for a in arrs) * dim
         enc = np.zeros(cap, np.float32) if want_encoder else None
         lg = np.zeros((logits_steps, n, vocab), np.float32) if logits_steps > 0 else None
         toks = np.zeros((n, max_tokens), np.int32)

@@ -57,6 +57,7 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else if (name == "max_tokens_per_second") out.max_tokens_per_second = float_from_string(value);
     else if (name == "decode_incomplete_lines") out.decode_incomplete_lines = bool_from_string(value);
     else if (name == "return_audio_data") out.return_audio_data = bool_from_string(value);
+    else if (name == "use_speculative_decoding") out.use_speculative_decoding = bool_from_string(value);
     else if (name == "log_output_text") out.log_output_text = bool_from_string(value);
     else if (name == "word_timestamps") out.word_timestamps = bool_from_string(value);
     else if (name == "identify_speakers") out.identify_speakers = bool_from_string(value);
@@ -64,7 +65,7 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else if (name == "context") out.context = value;
     else if (name == "device") out.device = int_from_string(value);  // additive
     // accepted for compatibility, no effect on this runtime (ORT / CPU-side features)
-    else if (name == "save_input_wav_path" || name == "log_ort_run" || name == "use_speculative_decoding" ||
+    else if (name == "save_input_wav_path" || name == "log_ort_run" ||
              name == "keyterm_boost" || name == "context_max_terms" || name == "diarization_cluster_cadence" ||
              name == "diarization_analyze_cadence" || name == "diarization_cluster_window_sec" ||
              name == "diarization_model_dir" || name == "spelling_model_path" || name == "ort_providers" ||
@@ -75,11 +76,6 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
   if (out.word_timestamps) {
     MSB_LOGF("word_timestamps is accepted but not produced by moonshine-b200 yet (words stay NULL)");
   }
-}
-
-bool is_streaming_arch(uint32_t arch) {
-  return arch == MOONSHINE_MODEL_ARCH_TINY_STREAMING || arch == MOONSHINE_MODEL_ARCH_BASE_STREAMING ||
-         arch == MOONSHINE_MODEL_ARCH_SMALL_STREAMING || arch == MOONSHINE_MODEL_ARCH_MEDIUM_STREAMING;
 }
 
 int32_t register_transcriber(Transcriber* t) {
@@ -159,10 +155,7 @@ int32_t moonshine_load_transcriber_from_files(const char* path, uint32_t model_a
     parse_options(options, options_count, opts);
     if (g_log_api_calls) MSB_LOGF("moonshine_load_transcriber_from_files(path=%s, model_arch=%u)", path ? path : "(null)", model_arch);
     if (!opts.skip_transcription) {
-      if (is_streaming_arch(model_arch)) {
-        throw std::runtime_error("Streaming model architectures are not implemented by moonshine-b200 yet");
-      }
-      dims_for_arch(model_arch);  // validates
+      if (!is_streaming_arch(model_arch)) dims_for_arch(model_arch);  // validates
       if (path == nullptr) throw std::runtime_error("Model path is null");
     }
     t = new Transcriber(opts, model_arch);
@@ -219,10 +212,7 @@ int32_t moonshine_load_transcriber_from_memory_files(const char** filenames, con
       }
     }
     if (!opts.skip_transcription) {
-      if (is_streaming_arch(model_arch)) {
-        throw std::runtime_error("Streaming model architectures are not implemented by moonshine-b200 yet");
-      }
-      dims_for_arch(model_arch);
+      if (!is_streaming_arch(model_arch)) dims_for_arch(model_arch);
       if (wbytes == nullptr) throw std::runtime_error("Missing required asset 'model.msw'");
       if (tbytes == nullptr) throw std::runtime_error("Missing required asset 'tokenizer.bin'");
     }
@@ -383,6 +373,13 @@ int32_t moonshine_b200_set_timing(int32_t transcriber_handle, int32_t enabled) {
   CHECK_HANDLE(t, transcriber_handle);
   if (t->model() == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
   t->model()->set_timing(enabled != 0);
+  return MOONSHINE_ERROR_NONE;
+}
+
+int32_t moonshine_b200_debug_stream_partial(int32_t transcriber_handle, int32_t enabled) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  t->model()->set_debug_stream_partial(enabled != 0);
   return MOONSHINE_ERROR_NONE;
 }
 

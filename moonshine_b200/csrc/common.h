@@ -54,7 +54,46 @@ struct Dims {
   float rope_theta = 10000.0f;
   int bos = 1;
   int eos = 2;
+  // --- streaming family (arch 2..5 and unit-test ids 102/103): dimensions are data, read from the
+  // weight container's "streaming.config" record (the reference reads streaming_config.json,
+  // core/moonshine-streaming-model.cpp:75-116) ---
+  bool streaming = false;
+  int enc_dim = 0;       // encoder hidden size E (adapter projects E -> D when different)
+  int enc_ffn = 0;
+  bool tied = true;      // logits off embed_tokens, else off proj_out
+  int max_seq_len = 448;
+  int max_pos_emb = 4096;
+  int n_windows = 0;
+  int win_past[16] = {0}, win_future[16] = {0};  // per encoder layer, inclusive
+  int lookahead() const {
+    int s = 0;
+    for (int i = 0; i < n_windows; i++) s += win_future[i];
+    return s;
+  }
 };
+
+inline bool is_streaming_arch(uint32_t arch) { return (arch >= 2 && arch <= 5) || arch == 102 || arch == 103; }
+
+// streaming.config: [version, E, D, enc_layers, dec_layers, H, hd, enc_ffn, ffn, vocab, rope_den, rot_dim,
+//                    rope_theta, tied, max_seq_len, max_pos_emb, bos, eos, n_windows, (past, future)...]
+inline Dims dims_from_streaming_config(uint32_t arch, const float* c, size_t n) {
+  if (n < 19 || c[0] != 1.0f) throw std::runtime_error("streaming.config: unsupported record");
+  Dims d;
+  d.arch = (int)arch;
+  d.streaming = true;
+  d.enc_dim = (int)c[1]; d.dim = (int)c[2]; d.enc_layers = (int)c[3]; d.dec_layers = (int)c[4];
+  d.heads = (int)c[5]; d.head_dim = (int)c[6]; d.enc_ffn = (int)c[7]; d.ffn = (int)c[8];
+  d.vocab = (int)c[9]; d.rope_den = (int)c[10]; d.rot_dim = (int)c[11]; d.rope_theta = c[12];
+  d.tied = c[13] != 0.0f; d.max_seq_len = (int)c[14]; d.max_pos_emb = (int)c[15];
+  d.bos = (int)c[16]; d.eos = (int)c[17]; d.n_windows = (int)c[18];
+  if (d.n_windows != d.enc_layers || d.n_windows > 16 || n < (size_t)19 + 2 * d.n_windows)
+    throw std::runtime_error("streaming.config: one (past, future) window per encoder layer expected");
+  for (int i = 0; i < d.n_windows; i++) {
+    d.win_past[i] = (int)c[19 + 2 * i];
+    d.win_future[i] = (int)c[20 + 2 * i];
+  }
+  return d;
+}
 
 inline Dims dims_for_arch(uint32_t arch) {
   Dims d;
@@ -71,6 +110,8 @@ inline Dims dims_for_arch(uint32_t arch) {
     case 100: set(64, 2, 2, 4, 16, 96, 512); break;      // unit-test config "test"
     case 101: set(72, 2, 3, 2, 36, 80, 300); break;      // unit-test config "test2"
     default:
+      if (is_streaming_arch(arch))
+        throw std::runtime_error(format("architecture %u takes its dimensions from the weight file", arch));
       throw std::runtime_error(format("Unsupported model architecture %u", arch));
   }
   return d;

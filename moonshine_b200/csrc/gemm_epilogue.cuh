@@ -43,6 +43,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, const RowCt
     float x = acc[j] * p.alpha;
     if (p.bias) x += p.bias_on_m ? r.bias_m : ((n + j < Nz) ? p.bias[n + j] : 0.f);
     if (p.act == 1) x = gelu_erf(x);
+    else if (p.act == 2) x = x / (1.0f + expf(-x));  // SiLU
     v[j] = x;
   }
   if (p.pos && n < p.rope_cols) {

@@ -31,7 +31,7 @@ struct GemmParams {
   float alpha = 1.0f;
   const float* bias = nullptr;  // indexed by n (or by m when bias_on_m)
   int bias_on_m = 0;
-  int act = 0;                  // 0 = none, 1 = exact-erf GELU
+  int act = 0;                  // 0 = none, 1 = exact-erf GELU, 2 = SiLU
   int accumulate = 0;           // C += result (fp32 output only)
   int out_half = 0;             // store __half instead of float
   // output addressing: addr = offC + rowoff(m) + coloff(n)
@@ -77,8 +77,22 @@ void launch_layernorm(const float* x, float* y, const float* gamma, int64_t rows
                       cudaStream_t stream);
 // In-place softmax over the first n_z columns of each row of group z's
 // [m_z, ld] score matrix; columns [n_z, ld) are zeroed.
+// win_past >= 0 restricts row m to columns m - win_past .. m + win_future (inclusive, the streaming
+// encoder's sliding window); columns outside get probability 0.
 void launch_softmax_rows(float* S, const int64_t* offS, const int* Mz, const int* Nz, int ld,
-                         int groups, int max_m, cudaStream_t stream);
+                         int groups, int max_m, cudaStream_t stream, int win_past = -1, int win_future = 0);
+
+// ---------------------------------------------------------------------------
+// Streaming frontend / adapter
+// ---------------------------------------------------------------------------
+// Per 80-sample frame: CMVN ((x - mean) / sqrt(mean((x - mean)^2) + 1e-6)), then asinh(k * x).
+// Frame f of utterance b is read at pcm + b * stride + f * 80 and written to out row
+// row0[b] + f (80 floats per row).
+void launch_stream_frames(const float* pcm, int64_t pcm_stride, const int* n_frames, const int64_t* row0,
+                          float k, float* out, int B, int max_frames, cudaStream_t stream);
+// y[r] = x[r] + table[pos[r]]  (rows of width D)
+void launch_add_rows_by_index(const float* x, const float* table, const int* pos, float* y, int64_t rows,
+                              int D, cudaStream_t stream);
 void launch_gelu_inplace(float* x, int64_t n, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------

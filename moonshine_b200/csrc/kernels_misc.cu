@@ -3,6 +3,8 @@
 
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace msb {
 
 namespace {
@@ -170,26 +172,80 @@ __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict_
 // grid (ceil(max_m / warps), groups); one warp per score row.
 __global__ void softmax_rows_kernel(float* __restrict__ S, const int64_t* __restrict__ offS,
                                     const int* __restrict__ Mz, const int* __restrict__ Nz,
-                                    int ld) {
+                                    int ld, int win_past, int win_future) {
   const int z = blockIdx.y;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= Mz[z]) return;
   const int n = Nz[z];
   const int lane = threadIdx.x & 31;
   float* row = S + offS[z] + (int64_t)m * ld;
+  // allowed columns [lo, hi)
+  int lo = 0, hi = n;
+  if (win_past >= 0) {
+    lo = max(0, m - win_past);
+    hi = min(n, m + win_future + 1);
+  }
   float mx = -INFINITY;
-  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
+  for (int j = lo + lane; j < hi; j += 32) mx = fmaxf(mx, row[j]);
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int j = lane; j < n; j += 32) {
+  for (int j = lo + lane; j < hi; j += 32) {
     const float e = expf(row[j] - mx);
     row[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  for (int j = lane; j < n; j += 32) row[j] *= inv;
-  for (int j = n + lane; j < ld; j += 32) row[j] = 0.f;
+  for (int j = lo + lane; j < hi; j += 32) row[j] *= inv;
+  for (int j = lane; j < lo; j += 32) row[j] = 0.f;
+  for (int j = hi + lane; j < ld; j += 32) row[j] = 0.f;
+}
+
+// one warp per 80-sample frame
+__global__ void stream_frames_kernel(const float* __restrict__ pcm, int64_t pcm_stride,
+                                     const int* __restrict__ n_frames, const int64_t* __restrict__ row0,
+                                     float k, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n_frames[b]) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = pcm + (int64_t)b * pcm_stride + (int64_t)f * 80;
+  float v[3];
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+    const int i = lane + 32 * u;
+    v[u] = i < 80 ? src[i] : 0.f;
+    s += v[u];
+  }
+  const float mean = warp_sum(s) * (1.0f / 80.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+    const int i = lane + 32 * u;
+    v[u] = i < 80 ? v[u] - mean : 0.f;
+    q += v[u] * v[u];
+  }
+  const float rms = sqrtf(warp_sum(q) * (1.0f / 80.0f) + 1e-6f);
+  float* dst = out + (row0[b] + f) * 80;
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+    const int i = lane + 32 * u;
+    if (i < 80) dst[i] = asinhf(k * (v[u] / rms));
+  }
+}
+
+__global__ void add_rows_by_index_kernel(const float* __restrict__ x, const float* __restrict__ table,
+                                         const int* __restrict__ pos, float* __restrict__ y, int64_t rows,
+                                         int D4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * D4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D4;
+    const int c = (int)(i - r * D4);
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 t = reinterpret_cast<const float4*>(table)[(int64_t)pos[r] * D4 + c];
+    reinterpret_cast<float4*>(y)[i] = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+  }
 }
 
 __global__ void gelu_inplace_kernel(float* x, int64_t n) {
@@ -236,11 +292,27 @@ void launch_layernorm(const float* x, float* y, const float* gamma, int64_t rows
 }
 
 void launch_softmax_rows(float* S, const int64_t* offS, const int* Mz, const int* Nz, int ld,
-                         int groups, int max_m, cudaStream_t stream) {
+                         int groups, int max_m, cudaStream_t stream, int win_past, int win_future) {
   if (groups == 0 || max_m == 0) return;
   const int warps = 8;
   dim3 grid((max_m + warps - 1) / warps, groups);
-  softmax_rows_kernel<<<grid, warps * 32, 0, stream>>>(S, offS, Mz, Nz, ld);
+  softmax_rows_kernel<<<grid, warps * 32, 0, stream>>>(S, offS, Mz, Nz, ld, win_past, win_future);
+}
+
+void launch_stream_frames(const float* pcm, int64_t pcm_stride, const int* n_frames, const int64_t* row0,
+                          float k, float* out, int B, int max_frames, cudaStream_t stream) {
+  if (B == 0 || max_frames == 0) return;
+  const int warps = 8;
+  dim3 grid((max_frames + warps - 1) / warps, B);
+  stream_frames_kernel<<<grid, warps * 32, 0, stream>>>(pcm, pcm_stride, n_frames, row0, k, out);
+}
+
+void launch_add_rows_by_index(const float* x, const float* table, const int* pos, float* y, int64_t rows,
+                              int D, cudaStream_t stream) {
+  if (rows == 0) return;
+  const int64_t n = rows * (D / 4);
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  add_rows_by_index_kernel<<<blocks, 256, 0, stream>>>(x, table, pos, y, rows, D / 4);
 }
 
 void launch_gelu_inplace(float* x, int64_t n, cudaStream_t stream) {

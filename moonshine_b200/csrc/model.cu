@@ -85,17 +85,25 @@ void Model::build_weights(const WeightFile& wf) {
 
   BlobBuilder bb;
   const std::string e = "model.encoder.";
+  const int E = d_.streaming ? d_.enc_dim : D;      // encoder hidden size
+  const int EI = d_.streaming ? d_.enc_ffn : I;
+  if (E % 4 || EI % 4 || E % H || (E / H) % 4) throw std::runtime_error("encoder dims must be multiples of 4");
+  size_t o_w1t = 0, o_gnw = 0, o_gnb = 0, o_c2 = 0, o_c2b = 0, o_c3 = 0, o_c3b = 0, o_encln = 0;
+  size_t o_slin = 0, o_sc1 = 0, o_sc1b = 0, o_sc2 = 0, o_sc2b = 0, o_pos = 0, o_proj = 0;
+  struct EncOff { size_t ln1, wqk, wv, wo, ln2, w1, b1, w2, b2; };
+  std::vector<EncOff> eo(d_.enc_layers);
+  if (!d_.streaming) {
   // conv1 [D][1][127] -> [127][D]
-  size_t o_w1t = bb.add((size_t)127 * D);
+  o_w1t = bb.add((size_t)127 * D);
   {
     const float* w = wf.get(e + "conv1.weight", {D, 1, 127}).data;
     for (int c = 0; c < D; c++)
       for (int j = 0; j < 127; j++) bb.data[o_w1t + (size_t)j * D + c] = w[(size_t)c * 127 + j];
   }
-  size_t o_gnw = bb.add_copy(wf.get(e + "groupnorm.weight", {D}).data, D);
-  size_t o_gnb = bb.add_copy(wf.get(e + "groupnorm.bias", {D}).data, D);
+  o_gnw = bb.add_copy(wf.get(e + "groupnorm.weight", {D}).data, D);
+  o_gnb = bb.add_copy(wf.get(e + "groupnorm.bias", {D}).data, D);
   // conv2 [2D][D][7] -> [2D][7*D] with K index = k*D + c (channel-last windows)
-  size_t o_c2 = bb.add((size_t)2 * D * 7 * D);
+  o_c2 = bb.add((size_t)2 * D * 7 * D);
   {
     const float* w = wf.get(e + "conv2.weight", {2 * D, D, 7}).data;
     for (int o = 0; o < 2 * D; o++)
@@ -103,8 +111,8 @@ void Model::build_weights(const WeightFile& wf) {
         for (int k = 0; k < 7; k++)
           bb.data[o_c2 + ((size_t)o * 7 + k) * D + c] = w[((size_t)o * D + c) * 7 + k];
   }
-  size_t o_c2b = bb.add_copy(wf.get(e + "conv2.bias", {2 * D}).data, 2 * D);
-  size_t o_c3 = bb.add((size_t)D * 3 * 2 * D);
+  o_c2b = bb.add_copy(wf.get(e + "conv2.bias", {2 * D}).data, 2 * D);
+  o_c3 = bb.add((size_t)D * 3 * 2 * D);
   {
     const float* w = wf.get(e + "conv3.weight", {D, 2 * D, 3}).data;
     for (int o = 0; o < D; o++)
@@ -112,10 +120,8 @@ void Model::build_weights(const WeightFile& wf) {
         for (int k = 0; k < 3; k++)
           bb.data[o_c3 + ((size_t)o * 3 + k) * 2 * D + c] = w[((size_t)o * 2 * D + c) * 3 + k];
   }
-  size_t o_c3b = bb.add_copy(wf.get(e + "conv3.bias", {D}).data, D);
+  o_c3b = bb.add_copy(wf.get(e + "conv3.bias", {D}).data, D);
 
-  struct EncOff { size_t ln1, wqk, wv, wo, ln2, w1, b1, w2, b2; };
-  std::vector<EncOff> eo(d_.enc_layers);
   for (int l = 0; l < d_.enc_layers; l++) {
     const std::string p = e + "layers." + std::to_string(l) + ".";
     eo[l].ln1 = bb.add_copy(wf.get(p + "input_layernorm.weight", {D}).data, D);
@@ -130,12 +136,59 @@ void Model::build_weights(const WeightFile& wf) {
     eo[l].w2 = bb.add_copy(wf.get(p + "mlp.fc2.weight", {D, I}).data, (size_t)D * I);
     eo[l].b2 = bb.add_copy(wf.get(p + "mlp.fc2.bias", {D}).data, D);
   }
-  size_t o_encln = bb.add_copy(wf.get(e + "layer_norm.weight", {D}).data, D);
+  o_encln = bb.add_copy(wf.get(e + "layer_norm.weight", {D}).data, D);
+
+  } else {
+    // ---- streaming frontend (HF MoonshineStreamingEncoderEmbedder / lora/export.py:53-97) ----
+    const std::string em = e + "embedder.";
+    s_k_ = std::exp(wf.get(em + "comp.log_k").data[0]);
+    o_slin = bb.add_copy(wf.get(em + "linear.weight", {E, 80}).data, (size_t)E * 80);
+    // causal convs [C_out][C_in][5] -> [C_out][5 * C_in] with K index = k * C_in + c (channel-last windows)
+    auto relayout_conv = [&](const std::string& name, int co, int ci) {
+      const float* w = wf.get(name, {co, ci, 5}).data;
+      size_t o = bb.add((size_t)co * 5 * ci);
+      for (int oc = 0; oc < co; oc++)
+        for (int c = 0; c < ci; c++)
+          for (int k = 0; k < 5; k++) bb.data[o + ((size_t)oc * 5 + k) * ci + c] = w[((size_t)oc * ci + c) * 5 + k];
+      return o;
+    };
+    o_sc1 = relayout_conv(em + "conv1.weight", 2 * E, E);
+    o_sc1b = bb.add_copy(wf.get(em + "conv1.bias", {2 * E}).data, 2 * E);
+    o_sc2 = relayout_conv(em + "conv2.weight", E, 2 * E);
+    o_sc2b = bb.add_copy(wf.get(em + "conv2.bias", {E}).data, E);
+    // unit-offset LayerNorm: y = LN(x) * (gamma + 1)  (HF MoonshineStreamingLayerNorm)
+    auto add_gamma1 = [&](const std::string& name) {
+      const float* g = wf.get(name, {E}).data;
+      size_t o = bb.add(E);
+      for (int k = 0; k < E; k++) bb.data[o + k] = g[k] + 1.0f;
+      return o;
+    };
+    for (int l = 0; l < d_.enc_layers; l++) {
+      const std::string p = e + "layers." + std::to_string(l) + ".";
+      eo[l].ln1 = add_gamma1(p + "input_layernorm.gamma");
+      eo[l].wqk = bb.add((size_t)2 * E * E);
+      std::memcpy(&bb.data[eo[l].wqk], wf.get(p + "self_attn.q_proj.weight", {E, E}).data, sizeof(float) * E * E);
+      std::memcpy(&bb.data[eo[l].wqk + (size_t)E * E], wf.get(p + "self_attn.k_proj.weight", {E, E}).data, sizeof(float) * E * E);
+      eo[l].wv = bb.add_copy(wf.get(p + "self_attn.v_proj.weight", {E, E}).data, (size_t)E * E);
+      eo[l].wo = bb.add_copy(wf.get(p + "self_attn.o_proj.weight", {E, E}).data, (size_t)E * E);
+      eo[l].ln2 = add_gamma1(p + "post_attention_layernorm.gamma");
+      eo[l].w1 = bb.add_copy(wf.get(p + "mlp.fc1.weight", {EI, E}).data, (size_t)EI * E);
+      eo[l].b1 = bb.add_copy(wf.get(p + "mlp.fc1.bias", {EI}).data, EI);
+      eo[l].w2 = bb.add_copy(wf.get(p + "mlp.fc2.weight", {E, EI}).data, (size_t)E * EI);
+      eo[l].b2 = bb.add_copy(wf.get(p + "mlp.fc2.bias", {E}).data, E);
+    }
+    o_encln = add_gamma1(e + "final_norm.gamma");
+    // adapter (lora/export.py:130-144): position table + optional projection E -> D
+    o_pos = bb.add_copy(wf.get("model.decoder.pos_emb.weight", {d_.max_pos_emb, E}).data, (size_t)d_.max_pos_emb * E);
+    if (E != D) o_proj = bb.add_copy(wf.get("model.decoder.proj.weight", {D, E}).data, (size_t)D * E);
+  }
 
   // ---- decoder ----
   const std::string dd = "model.decoder.";
-  const float* emb = wf.get(dd + "embed_tokens.weight", {V, D}).data;
-  size_t o_emb = bb.add_copy(emb, (size_t)V * D);
+  const float* emb_in = wf.get(dd + "embed_tokens.weight", {V, D}).data;   // token embedding
+  size_t o_emb = bb.add_copy(emb_in, (size_t)V * D);
+  // logits head: the embedding when tied, else proj_out (lora/export.py:206-211)
+  const float* emb = (d_.streaming && !d_.tied) ? wf.get("proj_out.weight", {V, D}).data : emb_in;
   // LayerNorm weights are folded into the rows (k index) of the weight block that consumes the
   // normalised activations, so the decoder kernels normalise without an affine step:
   // LN(x) W = ((x - mu) * rstd) (diag(gamma) W).
@@ -264,8 +317,15 @@ void Model::build_weights(const WeightFile& wf) {
                              cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   const float* base = wblob_.ptr;
-  w1t_ = base + o_w1t; gn_w_ = base + o_gnw; gn_b_ = base + o_gnb;
-  conv2_w_ = base + o_c2; conv2_b_ = base + o_c2b; conv3_w_ = base + o_c3; conv3_b_ = base + o_c3b;
+  if (!d_.streaming) {
+    w1t_ = base + o_w1t; gn_w_ = base + o_gnw; gn_b_ = base + o_gnb;
+    conv2_w_ = base + o_c2; conv2_b_ = base + o_c2b; conv3_w_ = base + o_c3; conv3_b_ = base + o_c3b;
+  } else {
+    s_lin_w_ = base + o_slin; s_c1_w_ = base + o_sc1; s_c1_b_ = base + o_sc1b;
+    s_c2_w_ = base + o_sc2; s_c2_b_ = base + o_sc2b;
+    pos_emb_ = base + o_pos;
+    proj_w_ = (E != D) ? base + o_proj : nullptr;
+  }
   enc_.resize(d_.enc_layers);
   for (int l = 0; l < d_.enc_layers; l++) {
     enc_[l] = {base + eo[l].ln1, base + eo[l].wqk, base + eo[l].wv, base + eo[l].wo, base + eo[l].ln2,
@@ -310,11 +370,37 @@ void Model::ensure_rope(int max_pos) {
   rope_positions_ = n;
 }
 
+void Model::one_shot_stream_plan(uint64_t n_samples, float max_tps, uint64_t& analysed, int& emitted,
+                                 int& max_tokens) const {
+  analysed = n_samples / 1280 * 1280;         // whole chunks only (core/transcriber.cpp:1342-1343)
+  emitted = (int)(analysed / 320);            // is_final: every analysed feature is emitted
+  const float dur = (float)n_samples / 16000.0f;
+  max_tokens = std::min((int)std::ceil(dur * max_tps), 256);  // core/transcriber.cpp:1386-1390
+}
+
+const StreamPlan* Model::auto_plan(const uint64_t*& n_samples, int B, float max_tps, AutoPlan& ap) const {
+  ap.analysed.resize(B); ap.emitted.resize(B); ap.max_tokens.resize(B);
+  for (int b = 0; b < B; b++) {
+    one_shot_stream_plan(n_samples[b], max_tps, ap.analysed[b], ap.emitted[b], ap.max_tokens[b]);
+    if (debug_stream_partial_) ap.emitted[b] = std::max(0, ap.emitted[b] - d_.lookahead());
+    if (ap.emitted[b] < 1) {
+      throw std::runtime_error(format("Audio segment of %llu samples gives the streaming encoder no memory",
+                                      (unsigned long long)n_samples[b]));
+    }
+  }
+  ap.plan.emitted = ap.emitted.data();
+  ap.plan.max_tokens = ap.max_tokens.data();
+  n_samples = ap.analysed.data();
+  return &ap.plan;
+}
+
 void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B, float max_tps,
-                       std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg) {
+                       std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan) {
   CUDA_CHECK(cudaSetDevice(device_));
   tokens.clear();
   if (B <= 0) return;
+  AutoPlan ap;
+  if (d_.streaming && plan == nullptr) plan = auto_plan(n_samples, B, max_tps, ap);
   uint64_t max_n = 0;
   for (int b = 0; b < B; b++) max_n = std::max(max_n, n_samples[b]);
   const int64_t stride = (int64_t)((max_n + 3) / 4 * 4);
@@ -353,7 +439,7 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
     }
   }
   const auto t1 = std::chrono::steady_clock::now();
-  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg);
+  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg, plan);
   if (std::getenv("MOONSHINE_B200_HOST_PROF")) {
     const auto t2 = std::chrono::steady_clock::now();
     MSB_LOGF("host profile: staging memcpy %.2f ms, h2d+run %.2f ms",
@@ -364,15 +450,17 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
 
 void Model::transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
                               float max_tps, std::vector<std::vector<int32_t>>& tokens,
-                              DebugCapture* dbg) {
+                              DebugCapture* dbg, const StreamPlan* plan) {
   CUDA_CHECK(cudaSetDevice(device_));
   tokens.clear();
   if (B <= 0) return;
-  run(d_pcm, stride, n_samples, B, max_tps, tokens, dbg);
+  AutoPlan ap;
+  if (d_.streaming && plan == nullptr) plan = auto_plan(n_samples, B, max_tps, ap);
+  run(d_pcm, stride, n_samples, B, max_tps, tokens, dbg, plan);
 }
 
 void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
-                std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg) {
+                std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan) {
   const int D = d_.dim, I = d_.ffn, H = d_.heads, hd = d_.head_dim, V = d_.vocab;
   const int L = d_.dec_layers;
   times_ = StageTimes();
@@ -391,27 +479,54 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   };
 
   // ---------------- plan ----------------
-  std::vector<int> T1(B), T2(B), T3(B), mlen(B), nsamp(B);
-  std::vector<int64_t> off1(B);
-  int64_t tot1 = 0;
-  int maxT1 = 0, maxT3 = 0, max_steps = 0;
+  // Row layouts.  Classic: conv1 rows off1[b] + t (T1 padded to 6 so that conv2 / conv3 are plain strided
+  // GEMMs over the packed array), encoder rows r3[b] = off1[b] / 6.  Streaming: hidden frames at rows
+  // hrow[b] + 4 + f and conv1 outputs at yrow[b] + 4 + j -- the 4 rows in front of each utterance stay
+  // zero and are the causal left padding of the two k=5, s=2 convolutions -- encoder rows r3[b].
+  const bool S = d_.streaming;
+  const int E = S ? d_.enc_dim : D, EI = S ? d_.enc_ffn : I, ehd = E / H;
+  if (S && plan == nullptr) throw std::runtime_error("streaming architectures need a StreamPlan");
+  std::vector<int> T1(B), T2(B), T3(B), Tm(B), mlen(B), nsamp(B), Fn(B), C1(B);
+  std::vector<int64_t> off1(B), hrow(B), yrow(B), r3v(B);
+  int64_t tot1 = 0, tot_h = 0, tot_y = 0, tot3 = 0;
+  int maxT1 = 0, maxT3 = 0, max_steps = 0, maxF = 0, maxC1 = 0;
   for (int b = 0; b < B; b++) {
     if (n_samples[b] == 0) throw std::runtime_error("Audio data is nullptr or empty");
     if (n_samples[b] > (uint64_t)INT32_MAX) throw std::runtime_error("Audio segment too long");
-    frontend_lengths((int64_t)n_samples[b], T1[b], T2[b], T3[b]);
-    if (T3[b] < 1) {
-      throw std::runtime_error(format("Audio segment of %llu samples is too short for the encoder",
-                                      (unsigned long long)n_samples[b]));
-    }
     nsamp[b] = (int)n_samples[b];
-    off1[b] = tot1;
-    tot1 += round_up(T1[b], 6);
+    if (!S) {
+      frontend_lengths((int64_t)n_samples[b], T1[b], T2[b], T3[b]);
+      if (T3[b] < 1) {
+        throw std::runtime_error(format("Audio segment of %llu samples is too short for the encoder",
+                                        (unsigned long long)n_samples[b]));
+      }
+      off1[b] = tot1;
+      r3v[b] = tot1 / 6;
+      tot1 += round_up(T1[b], 6);
+      Tm[b] = T3[b];
+      mlen[b] = max_len_for(n_samples[b], max_tps);
+    } else {
+      Fn[b] = nsamp[b] / 80;                       // whole 80-sample frames
+      C1[b] = Fn[b] >= 1 ? (Fn[b] - 1) / 2 + 1 : 0;  // causal k=5, s=2: floor((F + 4 - 5) / 2) + 1
+      T3[b] = C1[b] >= 1 ? (C1[b] - 1) / 2 + 1 : 0;
+      Tm[b] = plan->emitted[b];
+      mlen[b] = plan->max_tokens[b];
+      if (Tm[b] < 1 || Tm[b] > T3[b])
+        throw std::runtime_error(format("streaming segment %d: %d memory frames requested, %d analysed", b, Tm[b], T3[b]));
+      if (T3[b] > d_.max_pos_emb) throw std::runtime_error("streaming segment longer than the adapter position table");
+      if (mlen[b] > d_.max_seq_len) mlen[b] = d_.max_seq_len;
+      hrow[b] = tot_h; tot_h += 4 + Fn[b];
+      yrow[b] = tot_y; tot_y += 4 + C1[b];
+      r3v[b] = tot3; tot3 += round_up(T3[b], 4);
+      maxF = std::max(maxF, Fn[b]);
+      maxC1 = std::max(maxC1, C1[b]);
+    }
     maxT1 = std::max(maxT1, T1[b]);
     maxT3 = std::max(maxT3, T3[b]);
-    mlen[b] = max_len_for(n_samples[b], max_tps);
     max_steps = std::max(max_steps, mlen[b]);
   }
-  const int64_t tot2 = tot1 / 3, tot3 = tot1 / 6;
+  const int64_t tot2 = tot1 / 3;
+  if (!S) tot3 = tot1 / 6;
   const int Tp = round_up(maxT3, 4);      // encoder score / V^T row stride
   const int Tpad = round_up(maxT3, 8);    // decoder cross K/V time padding
   const int Smax = round_up(std::max(max_steps, 1) + 1, 4);
@@ -419,10 +534,11 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   ensure_rope(std::max(maxT3, Smax) + 1);
 
   // ---------------- metadata upload ----------------
-  // int32: nsamp[B] T1[B] T3[B] mlen[B] pos[tot3] MzT[BH] DzB[B]
+  // int32: nsamp[B] T1[B] T3[B] mlen[B] pos[tot3] MzT[BH] DzB[B] Tm[B] Fn[B] C1[B]
   // int64: off1[B] offQ[BH] offK[BH] offS[BH] offVh[BH] offO[BH] offXb[B] offVt[B] offKc[B] offVc[B]
-  const size_t n_i32 = (size_t)4 * B + tot3 + BH + B;
-  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B;
+  //        offMem[B] frRow[B] c1A[B] c1C[B] c2A[B] c2C[B]
+  const size_t n_i32 = (size_t)4 * B + tot3 + BH + B + 3 * B;
+  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B + 6 * B;
   pin_i32_.reserve(n_i32);
   pin_i64_.reserve(n_i64);
   meta_i32_.reserve(n_i32);
@@ -433,28 +549,38 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   int *h_ns = pi, *h_t1 = pi + B, *h_t3 = pi + 2 * B, *h_ml = pi + 3 * B, *h_pos = pi + 4 * B;
   int* h_mzt = h_pos + tot3;
   int* h_dzb = h_mzt + BH;
+  int *h_tm = h_dzb + B, *h_fn = h_tm + B, *h_c1 = h_fn + B;
   int64_t *h_off1 = pl, *h_offq = pl + B, *h_offk = h_offq + BH, *h_offs = h_offk + BH,
           *h_offvh = h_offs + BH, *h_offo = h_offvh + BH, *h_offxb = h_offo + BH,
           *h_offvt = h_offxb + B, *h_offkc = h_offvt + B, *h_offvc = h_offkc + B;
+  int64_t *h_offmem = h_offvc + B, *h_frrow = h_offmem + B, *h_c1a = h_frrow + B, *h_c1c = h_c1a + B,
+          *h_c2a = h_c1c + B, *h_c2c = h_c2a + B;
   std::memset(h_pos, 0, sizeof(int) * tot3);
   for (int b = 0; b < B; b++) {
     h_ns[b] = nsamp[b]; h_t1[b] = T1[b]; h_t3[b] = T3[b]; h_ml[b] = mlen[b];
+    h_tm[b] = Tm[b]; h_fn[b] = Fn[b]; h_c1[b] = C1[b];
     h_off1[b] = off1[b];
-    const int64_t r3 = off1[b] / 6;
+    const int64_t r3 = r3v[b];
     for (int t = 0; t < T3[b]; t++) h_pos[r3 + t] = t;
-    h_dzb[b] = D;
-    h_offxb[b] = r3 * D;
-    h_offvt[b] = (int64_t)b * D * Tp;
+    h_dzb[b] = E;
+    h_offxb[b] = r3 * E;
+    h_offmem[b] = r3 * D;
+    h_offvt[b] = (int64_t)b * E * Tp;
     h_offkc[b] = (int64_t)b * H * hd * Tpad;
     h_offvc[b] = (int64_t)b * H * Tpad * hd;
+    h_frrow[b] = hrow[b] + 4;
+    h_c1a[b] = hrow[b] * E;
+    h_c1c[b] = (yrow[b] + 4) * 2 * E;
+    h_c2a[b] = yrow[b] * 2 * E;
+    h_c2c[b] = r3 * E;
     for (int h = 0; h < H; h++) {
       const int z = b * H + h;
       h_mzt[z] = T3[b];
-      h_offq[z] = r3 * 2 * D + (int64_t)h * hd;
-      h_offk[z] = r3 * 2 * D + D + (int64_t)h * hd;
+      h_offq[z] = r3 * 2 * E + (int64_t)h * ehd;
+      h_offk[z] = r3 * 2 * E + E + (int64_t)h * ehd;
       h_offs[z] = (int64_t)z * maxT3 * Tp;
-      h_offvh[z] = (int64_t)b * D * Tp + (int64_t)h * hd * Tp;
-      h_offo[z] = r3 * D + (int64_t)h * hd;
+      h_offvh[z] = (int64_t)b * E * Tp + (int64_t)h * ehd * Tp;
+      h_offo[z] = r3 * E + (int64_t)h * ehd;
     }
   }
   CUDA_CHECK(cudaMemcpyAsync(meta_i32_.ptr, pi, n_i32 * sizeof(int), cudaMemcpyHostToDevice, stream_));
@@ -462,10 +588,13 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   const int* d_ns = meta_i32_.ptr;
   const int *d_t1 = d_ns + B, *d_t3 = d_ns + 2 * B, *d_ml = d_ns + 3 * B, *d_pos = d_ns + 4 * B;
   const int* d_mzt = d_pos + tot3;
+  const int *d_tm = d_mzt + BH + B, *d_fn = d_tm + B, *d_c1 = d_fn + B;
   const int64_t* d_off1 = meta_i64_.ptr;
   const int64_t *d_offq = d_off1 + B, *d_offk = d_offq + BH, *d_offs = d_offk + BH,
                 *d_offvh = d_offs + BH, *d_offo = d_offvh + BH, *d_offxb = d_offo + BH,
                 *d_offvt = d_offxb + B, *d_offkc = d_offvt + B, *d_offvc = d_offkc + B;
+  const int64_t *d_offmem = d_offvc + B, *d_frrow = d_offmem + B, *d_c1a = d_frrow + B, *d_c1c = d_c1a + B,
+                *d_c2a = d_c1c + B, *d_c2c = d_c2a + B;
 
   // ---------------- workspaces ----------------
   auto reserve_zero = [&](DeviceBuffer<float>& buf, size_t n) {
@@ -474,31 +603,40 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       CUDA_CHECK(cudaMemsetAsync(buf.ptr, 0, buf.bytes(), stream_));
     }
   };
-  reserve_zero(h1_, (size_t)(tot1 + 8) * D);
-  reserve_zero(h2_, (size_t)(tot2 + 4) * 2 * D);
-  reserve_zero(x_, (size_t)tot3 * D);
-  reserve_zero(ln_, (size_t)tot3 * D);
-  reserve_zero(qk_, (size_t)tot3 * 2 * D);
-  reserve_zero(vt_, (size_t)B * D * Tp);
+  if (!S) {
+    reserve_zero(h1_, (size_t)(tot1 + 8) * D);
+    reserve_zero(h2_, (size_t)(tot2 + 4) * 2 * D);
+  } else {
+    reserve_zero(frames_, (size_t)(tot_h + 8) * 80);
+    reserve_zero(h1_, (size_t)(tot_h + 8) * E);
+    reserve_zero(h2_, (size_t)(tot_y + 8) * 2 * E);
+    // the 4 rows in front of every utterance are the convolutions' zero padding
+    CUDA_CHECK(cudaMemsetAsync(frames_.ptr, 0, (size_t)tot_h * 80 * sizeof(float), stream_));
+    CUDA_CHECK(cudaMemsetAsync(h2_.ptr, 0, (size_t)tot_y * 2 * E * sizeof(float), stream_));
+  }
+  reserve_zero(x_, (size_t)tot3 * E);
+  reserve_zero(ln_, (size_t)tot3 * E);
+  reserve_zero(qk_, (size_t)tot3 * 2 * E);
+  reserve_zero(vt_, (size_t)B * E * Tp);
   reserve_zero(scores_, (size_t)BH * maxT3 * Tp);
-  reserve_zero(attn_, (size_t)tot3 * D);
-  reserve_zero(mid_, (size_t)tot3 * I);
-  reserve_zero(enc_out_, (size_t)tot3 * D);
-  const int nblk = conv1_blocks_per_utt(maxT1);
-  gn_partial_.reserve((size_t)B * nblk * 2);
+  reserve_zero(attn_, (size_t)tot3 * E);
+  reserve_zero(mid_, (size_t)tot3 * EI);
+  reserve_zero(enc_out_, (size_t)tot3 * std::max(D, E));
+  const int nblk = S ? 0 : conv1_blocks_per_utt(maxT1);
+  if (!S) gn_partial_.reserve((size_t)B * nblk * 2);
   // V^T padding columns must stay finite: re-zero when the layout changes
-  CUDA_CHECK(cudaMemsetAsync(vt_.ptr, 0, (size_t)B * D * Tp * sizeof(float), stream_));
+  CUDA_CHECK(cudaMemsetAsync(vt_.ptr, 0, (size_t)B * E * Tp * sizeof(float), stream_));
 
   stage("setup", -1, 1);
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
   // ---------------- frontend ----------------
-  launch_conv1_tanh(d_pcm, stride, d_ns, d_t1, d_off1, w1t_, h1_.ptr, D, B, maxT1, gn_partial_.ptr,
-                    nullptr, stream_);
-  stage("conv1", -1, 2);
-  launch_groupnorm_apply(h1_.ptr, d_t1, d_off1, gn_partial_.ptr, nblk, gn_w_, gn_b_, D, B, maxT1, stream_);
-  stage("groupnorm", -1, 2);
-  launches += 2;
-  {
+  if (!S) {
+    launch_conv1_tanh(d_pcm, stride, d_ns, d_t1, d_off1, w1t_, h1_.ptr, D, B, maxT1, gn_partial_.ptr,
+                      nullptr, stream_);
+    stage("conv1", -1, 2);
+    launch_groupnorm_apply(h1_.ptr, d_t1, d_off1, gn_partial_.ptr, nblk, gn_w_, gn_b_, D, B, maxT1, stream_);
+    stage("groupnorm", -1, 2);
+    launches += 2;
     // conv2 as a GEMM over overlapping row windows of the channel-last h1:
     // output row r reads h1 rows 3r .. 3r+6 (7*D contiguous floats).
     GemmParams g;
@@ -512,78 +650,125 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     launch_gemm(g3, stream_);
     stage("conv3", -1, 2);
     launches += 2;
+  } else {
+    // frames -> CMVN -> asinh (one warp per frame), then Linear(80 -> E) + SiLU as one GEMM over every
+    // row of the padded layout: padding rows of `frames_` are zero and the linear has no bias, so the
+    // padding rows of the hidden array come out as exact zeros.
+    launch_stream_frames(d_pcm, stride, d_fn, d_frrow, s_k_, frames_.ptr, B, maxF, stream_);
+    stage("stream_frames", -1, 2);
+    GemmParams g;
+    g.A = frames_.ptr; g.lda = 80; g.W = s_lin_w_; g.ldw = 80; g.C = h1_.ptr; g.rs = E;
+    g.M = (int)tot_h; g.N = E; g.K = 80; g.act = 2;
+    launch_gemm(g, stream_);
+    stage("stream_linear", -1, 2);
+    // causal conv1 (E -> 2E, k=5, s=2) + SiLU: output j of utterance b reads hidden rows hrow[b] + 2j ..
+    // + 4 (5 * E contiguous floats); grouped per utterance so the padding rows of the output stay zero.
+    GemmParams c1;
+    c1.A = h1_.ptr; c1.lda = 2 * E; c1.offA = d_c1a; c1.W = s_c1_w_; c1.ldw = 5 * E; c1.strideW = 0;
+    c1.C = h2_.ptr; c1.offC = d_c1c; c1.rs = 2 * E;
+    c1.groups = B; c1.M = maxC1; c1.N = 2 * E; c1.K = 5 * E; c1.Mz = d_c1; c1.bias = s_c1_b_; c1.act = 2;
+    launch_gemm(c1, stream_);
+    stage("stream_conv1", -1, 2);
+    GemmParams c2;
+    c2.A = h2_.ptr; c2.lda = 2 * 2 * E; c2.offA = d_c2a; c2.W = s_c2_w_; c2.ldw = 5 * 2 * E; c2.strideW = 0;
+    c2.C = x_.ptr; c2.offC = d_c2c; c2.rs = E;
+    c2.groups = B; c2.M = maxT3; c2.N = E; c2.K = 5 * 2 * E; c2.Mz = d_t3; c2.bias = s_c2_b_;
+    launch_gemm(c2, stream_);
+    stage("stream_conv2", -1, 2);
+    launches += 4;
   }
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
 
   // ---------------- encoder layers ----------------
-  const float scale = 1.0f / std::sqrt((float)hd);
+  const float scale = 1.0f / std::sqrt((float)ehd);
   for (int l = 0; l < d_.enc_layers; l++) {
     const EncLayer& w = enc_[l];
-    launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, D, stream_);
-    {  // Q|K projection with fused interleaved RoPE
+    launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, E, stream_);
+    {  // Q|K projection (classic: with fused interleaved RoPE; the streaming encoder has no positions)
       GemmParams g;
-      g.A = ln_.ptr; g.lda = D; g.W = w.wqk; g.ldw = D; g.C = qk_.ptr; g.rs = 2 * D;
-      g.M = (int)tot3; g.N = 2 * D; g.K = D;
-      g.pos = d_pos; g.rope_cos = rope_cos_.ptr; g.rope_sin = rope_sin_.ptr;
-      g.rope_cols = 2 * D; g.head_dim = hd; g.rot_dim = d_.rot_dim;
+      g.A = ln_.ptr; g.lda = E; g.W = w.wqk; g.ldw = E; g.C = qk_.ptr; g.rs = 2 * E;
+      g.M = (int)tot3; g.N = 2 * E; g.K = E;
+      if (!S) {
+        g.pos = d_pos; g.rope_cos = rope_cos_.ptr; g.rope_sin = rope_sin_.ptr;
+        g.rope_cols = 2 * E; g.head_dim = ehd; g.rot_dim = d_.rot_dim;
+      }
       launch_gemm(g, stream_);
     }
-    {  // V^T_b[D, T_b] = Wv * ln_b^T  (swapped orientation, per utterance)
+    {  // V^T_b[E, T_b] = Wv * ln_b^T  (swapped orientation, per utterance)
       GemmParams g;
-      g.A = w.wv; g.lda = D; g.strideA = 0; g.W = ln_.ptr; g.ldw = D; g.offW = d_offxb;
+      g.A = w.wv; g.lda = E; g.strideA = 0; g.W = ln_.ptr; g.ldw = E; g.offW = d_offxb;
       g.C = vt_.ptr; g.offC = d_offvt; g.rs = Tp;
-      g.groups = B; g.M = D; g.N = maxT3; g.K = D; g.Nz = d_t3;
+      g.groups = B; g.M = E; g.N = maxT3; g.K = E; g.Nz = d_t3;
       launch_gemm(g, stream_);
     }
     {  // S_z = scale * Q_z K_z^T
       GemmParams g;
-      g.A = qk_.ptr; g.lda = 2 * D; g.offA = d_offq; g.W = qk_.ptr; g.ldw = 2 * D; g.offW = d_offk;
+      g.A = qk_.ptr; g.lda = 2 * E; g.offA = d_offq; g.W = qk_.ptr; g.ldw = 2 * E; g.offW = d_offk;
       g.C = scores_.ptr; g.offC = d_offs; g.rs = Tp;
-      g.groups = BH; g.M = maxT3; g.N = maxT3; g.K = hd; g.Mz = d_mzt; g.Nz = d_mzt;
+      g.groups = BH; g.M = maxT3; g.N = maxT3; g.K = ehd; g.Mz = d_mzt; g.Nz = d_mzt;
       g.alpha = scale;
       launch_gemm(g, stream_);
     }
-    launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_);
+    if (S) launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_, d_.win_past[l], d_.win_future[l]);
+    else launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_);
     {  // O_z = P_z V_z
       GemmParams g;
       g.A = scores_.ptr; g.lda = Tp; g.offA = d_offs; g.W = vt_.ptr; g.ldw = Tp; g.offW = d_offvh;
-      g.C = attn_.ptr; g.offC = d_offo; g.rs = D;
-      g.groups = BH; g.M = maxT3; g.N = hd; g.K = maxT3; g.Mz = d_mzt; g.Kz = d_mzt;
+      g.C = attn_.ptr; g.offC = d_offo; g.rs = E;
+      g.groups = BH; g.M = maxT3; g.N = ehd; g.K = maxT3; g.Mz = d_mzt; g.Kz = d_mzt;
       launch_gemm(g, stream_);
     }
     {  // x += attn Wo^T
       GemmParams g;
-      g.A = attn_.ptr; g.lda = D; g.W = w.wo; g.ldw = D; g.C = x_.ptr; g.rs = D;
-      g.M = (int)tot3; g.N = D; g.K = D; g.accumulate = 1;
+      g.A = attn_.ptr; g.lda = E; g.W = w.wo; g.ldw = E; g.C = x_.ptr; g.rs = E;
+      g.M = (int)tot3; g.N = E; g.K = E; g.accumulate = 1;
       launch_gemm(g, stream_);
     }
-    launch_layernorm(x_.ptr, ln_.ptr, w.ln2, tot3, D, stream_);
+    launch_layernorm(x_.ptr, ln_.ptr, w.ln2, tot3, E, stream_);
     {
       GemmParams g;
-      g.A = ln_.ptr; g.lda = D; g.W = w.w1; g.ldw = D; g.C = mid_.ptr; g.rs = I;
-      g.M = (int)tot3; g.N = I; g.K = D; g.bias = w.b1; g.act = 1;
+      g.A = ln_.ptr; g.lda = E; g.W = w.w1; g.ldw = E; g.C = mid_.ptr; g.rs = EI;
+      g.M = (int)tot3; g.N = EI; g.K = E; g.bias = w.b1; g.act = 1;
       launch_gemm(g, stream_);
       GemmParams g2;
-      g2.A = mid_.ptr; g2.lda = I; g2.W = w.w2; g2.ldw = I; g2.C = x_.ptr; g2.rs = D;
-      g2.M = (int)tot3; g2.N = D; g2.K = I; g2.bias = w.b2; g2.accumulate = 1;
+      g2.A = mid_.ptr; g2.lda = EI; g2.W = w.w2; g2.ldw = EI; g2.C = x_.ptr; g2.rs = E;
+      g2.M = (int)tot3; g2.N = E; g2.K = EI; g2.bias = w.b2; g2.accumulate = 1;
       launch_gemm(g2, stream_);
     }
     launches += 10;
     stage("encoder_layer", l, 4);
   }
-  launch_layernorm(x_.ptr, enc_out_.ptr, enc_final_ln_, tot3, D, stream_);
-  launches += 1;
+  if (!S) {
+    launch_layernorm(x_.ptr, enc_out_.ptr, enc_final_ln_, tot3, D, stream_);
+    launches += 1;
+  } else {
+    // final unit-offset norm, then the adapter: memory = proj(encoded + pos_emb[frame index])
+    // (lora/export.py:130-144; every segment is encoded from its first frame, so the offset is 0)
+    launch_layernorm(x_.ptr, ln_.ptr, enc_final_ln_, tot3, E, stream_);
+    if (proj_w_ == nullptr) {
+      launch_add_rows_by_index(ln_.ptr, pos_emb_, d_pos, enc_out_.ptr, tot3, E, stream_);
+    } else {
+      launch_add_rows_by_index(ln_.ptr, pos_emb_, d_pos, attn_.ptr, tot3, E, stream_);
+      GemmParams g;
+      g.A = attn_.ptr; g.lda = E; g.W = proj_w_; g.ldw = E; g.C = enc_out_.ptr; g.rs = D;
+      g.M = (int)tot3; g.N = D; g.K = E;
+      launch_gemm(g, stream_);
+      launches += 1;
+    }
+    launches += 2;
+    stage("adapter", -1, 4);
+  }
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
 
   if (dbg && dbg->encoder_out) {
     dbg->encoder_out->clear();
-    if (dbg->encoder_frames) dbg->encoder_frames->assign(T3.begin(), T3.end());
+    if (dbg->encoder_frames) dbg->encoder_frames->assign(Tm.begin(), Tm.end());
     std::vector<float> all((size_t)tot3 * D);
     CUDA_CHECK(cudaMemcpyAsync(all.data(), enc_out_.ptr, all.size() * sizeof(float), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     for (int b = 0; b < B; b++) {
-      const float* src = all.data() + (size_t)(off1[b] / 6) * D;
-      dbg->encoder_out->insert(dbg->encoder_out->end(), src, src + (size_t)T3[b] * D);
+      const float* src = all.data() + (size_t)r3v[b] * D;
+      dbg->encoder_out->insert(dbg->encoder_out->end(), src, src + (size_t)Tm[b] * D);
     }
   }
   if (dbg && dbg->skip_decode) {
@@ -600,15 +785,15 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   CUDA_CHECK(cudaMemsetAsync(kc_.ptr, 0, kv_elems * sizeof(__half), stream_));
   {
     GemmParams g;  // K^T: rows (l, h, d), cols t
-    g.A = wk_all_; g.lda = D; g.W = enc_out_.ptr; g.ldw = D; g.offW = d_offxb;
+    g.A = wk_all_; g.lda = D; g.W = enc_out_.ptr; g.ldw = D; g.offW = d_offmem;
     g.C = kc_.ptr; g.offC = d_offkc; g.out_half = 1;
-    g.groups = B; g.M = L * D; g.N = maxT3; g.K = D; g.Nz = d_t3;
+    g.groups = B; g.M = L * D; g.N = maxT3; g.K = D; g.Nz = d_tm;
     g.rm1 = D; g.rs1 = (int64_t)B * H * hd * Tpad; g.rm2 = hd; g.rs2 = (int64_t)hd * Tpad; g.rs = Tpad;
     launch_gemm(g, stream_);
     GemmParams v;  // V: rows t, cols (l, h, d)
-    v.A = enc_out_.ptr; v.lda = D; v.offA = d_offxb; v.W = wv_all_; v.ldw = D;
+    v.A = enc_out_.ptr; v.lda = D; v.offA = d_offmem; v.W = wv_all_; v.ldw = D;
     v.C = vc_.ptr; v.offC = d_offvc; v.out_half = 1;
-    v.groups = B; v.M = maxT3; v.N = L * D; v.K = D; v.Mz = d_t3;
+    v.groups = B; v.M = maxT3; v.N = L * D; v.K = D; v.Mz = d_tm;
     v.rs = hd; v.cm1 = D; v.cs1 = (int64_t)B * H * Tpad * hd; v.cm2 = hd; v.cs2 = (int64_t)Tpad * hd;
     launch_gemm(v, stream_);
     launches += 2;
@@ -649,7 +834,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     CUDA_CHECK(cudaMemsetAsync(done_dev_.ptr, 0, B * sizeof(int), stream_));
   }
   p.rope_cos = rope_cos_.ptr; p.rope_sin = rope_sin_.ptr;
-  p.enc_len = d_t3; p.max_len = d_ml;
+  p.enc_len = d_tm; p.max_len = d_ml;
   p.kc = kc_.ptr; p.vc = vc_.ptr; p.ks = ks_.ptr; p.vs = vs_.ptr;
   p.hbuf = hbuf_.ptr; p.part = part_.ptr; p.xfin = xfin_.ptr;
   p.cand_val = cand_val_.ptr; p.cand_idx = cand_idx_.ptr;

@@ -26,6 +26,14 @@ struct DebugCapture {
   bool skip_decode = false;
 };
 
+// Streaming architectures: what the host bookkeeping (Transcriber, mirroring
+// core/transcriber.cpp:1331-1395) decided for each segment of the batch.  n_samples[b] passed beside it
+// is the number of ANALYSED samples (whole 1280-sample chunks).
+struct StreamPlan {
+  const int* emitted = nullptr;     // [B] encoder features that form the decoder memory (<= analysed / 320)
+  const int* max_tokens = nullptr;  // [B] decode budget
+};
+
 struct StageTimes {
   float frontend_ms = 0, encoder_ms = 0, cross_kv_ms = 0, decode_ms = 0;
   int decode_steps = 0;
@@ -45,17 +53,23 @@ class Model {
   // Host PCM (16 kHz mono float).  Copies to the device inside the call.
   void transcribe(const float* const* pcm, const uint64_t* n_samples, int B,
                   float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
-                  DebugCapture* dbg = nullptr);
+                  DebugCapture* dbg = nullptr, const StreamPlan* plan = nullptr);
   // Device-resident PCM: row b at d_pcm + b * stride.
   void transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
                          float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
-                         DebugCapture* dbg = nullptr);
+                         DebugCapture* dbg = nullptr, const StreamPlan* plan = nullptr);
+  // Streaming bookkeeping for a one-shot call on a complete segment of n samples
+  // (core/transcriber.cpp:1331-1390): analysed samples, emitted features, greedy token budget.
+  void one_shot_stream_plan(uint64_t n_samples, float max_tokens_per_second, uint64_t& analysed, int& emitted,
+                            int& max_tokens) const;
 
   // reference rule: core/moonshine-model.cpp:347-349
   static int max_len_for(uint64_t n_samples, float max_tokens_per_second);
 
   const StageTimes& last_times() const { return times_; }
   void set_timing(bool on) { timing_ = on; }
+  // parity hook: plan-less calls on a streaming model act as a NON-final update (look-ahead held back)
+  void set_debug_stream_partial(bool on) { debug_stream_partial_ = on; }
   size_t weight_bytes() const { return wblob_.bytes(); }
 
  private:
@@ -64,14 +78,22 @@ class Model {
   };
   void build_weights(const WeightFile& wf);
   void ensure_rope(int max_pos);
+  struct AutoPlan {
+    std::vector<uint64_t> analysed;
+    std::vector<int> emitted, max_tokens;
+    StreamPlan plan;
+  };
+  // plan-less call on a streaming model: one-shot bookkeeping per utterance
+  const StreamPlan* auto_plan(const uint64_t*& n_samples, int B, float max_tps, AutoPlan& ap) const;
   void run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
-           std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg);
+           std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan);
 
   Dims d_;
   int device_ = 0;
   int sm_count_ = 0;
   cudaStream_t stream_ = nullptr;
   bool timing_ = false;
+  bool debug_stream_partial_ = false;
   StageTimes times_;
   cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -81,6 +103,10 @@ class Model {
   const float *conv2_w_ = nullptr, *conv2_b_ = nullptr, *conv3_w_ = nullptr, *conv3_b_ = nullptr;
   std::vector<EncLayer> enc_;
   const float* enc_final_ln_ = nullptr;
+  // streaming frontend / adapter (null for the classic architectures)
+  const float *s_lin_w_ = nullptr, *s_c1_w_ = nullptr, *s_c1_b_ = nullptr, *s_c2_w_ = nullptr, *s_c2_b_ = nullptr;
+  const float *pos_emb_ = nullptr, *proj_w_ = nullptr;
+  float s_k_ = 1.0f;  // exp(log_k) of the asinh compression
   const float *wk_all_ = nullptr, *wv_all_ = nullptr;
   DecoderParams dec_{};  // weight pointers + dims prefilled
   int ffn_chunk_ = 64;
@@ -92,7 +118,7 @@ class Model {
   int rope_positions_ = 0;
 
   // workspaces (grow-only)
-  DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_;
+  DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_, frames_;
   DeviceBuffer<double> gn_partial_;
   DeviceBuffer<__half> kc_, vc_;
   DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_;

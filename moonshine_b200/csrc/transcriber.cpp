@@ -300,6 +300,13 @@ static int pick_device(int requested) {
   return dev;
 }
 
+// Classic architectures have fixed dimensions; the streaming family reads them from the container.
+static Dims dims_for(uint32_t arch, const WeightFile& wf) {
+  if (!is_streaming_arch(arch)) return dims_for_arch(arch);
+  const HostTensor& c = wf.get("streaming.config");
+  return dims_from_streaming_config(arch, c.data, c.count);
+}
+
 void Transcriber::load_from_directory(const std::string& path) {
   if (options_.skip_transcription) return;
   if (!dir_exists(path)) throw std::runtime_error("Model directory '" + path + "' does not exist");
@@ -319,7 +326,7 @@ void Transcriber::load_from_directory(const std::string& path) {
                                     wf.arch, arch_));
   }
   tokenizer_.reset(Tokenizer::from_file(tpath));
-  model_ = std::make_unique<Model>(dims_for_arch(arch_), wf, pick_device(options_.device));
+  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
 }
 
 void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
@@ -331,17 +338,19 @@ void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
     throw std::runtime_error(format("model.msw holds architecture %u but %u was requested", wf.arch, arch_));
   }
   tokenizer_ = std::make_unique<Tokenizer>(tokenizer, tokenizer_size);
-  model_ = std::make_unique<Model>(dims_for_arch(arch_), wf, pick_device(options_.device));
+  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
 }
 
 // One batched model call for every just_updated segment of every job.
 // Reference: Transcriber::update_transcript_from_segments
 // (core/transcriber.cpp:989-1148), which runs the segments serially.
 void Transcriber::update_outputs(std::vector<Job>& jobs) {
-  struct Pending { size_t job; size_t seg; Line line; bool run; };
+  struct Pending { size_t job; size_t seg; Line line; bool run; bool strip_eos; };
   std::vector<Pending> pend;
   std::vector<const float*> ptrs;
   std::vector<uint64_t> lens;
+  std::vector<int> plan_emitted, plan_max_tokens;   // streaming architectures only
+  const bool streaming = model_ && model_->dims().streaming;
   for (size_t j = 0; j < jobs.size(); j++) {
     jobs[j].output->clear_update_flags();
     std::vector<Segment>& segs = *jobs[j].segments;
@@ -349,7 +358,7 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
       Segment& s = segs[si];
       if (!s.just_updated) continue;
       Pending p;
-      p.job = j; p.seg = si; p.run = false;
+      p.job = j; p.seg = si; p.run = false; p.strip_eos = false;
       p.line.start_time = s.start_time;
       p.line.duration = s.end_time - s.start_time;
       p.line.is_complete = s.is_complete;
@@ -357,7 +366,40 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
       TranscriptOutput& out = *jobs[j].output;
       if (si >= out.order.size()) out.order.push_back(next_line_id_.fetch_add(1));
       p.line.id = out.order.at(si);
-      if (model_) {
+      if (streaming) {
+        // Host bookkeeping of transcribe_segment_with_streaming_model (core/transcriber.cpp:1331-1395) +
+        // MoonshineStreamingModel::encode (moonshine-streaming-model.cpp:611-640): only whole 1280-sample
+        // chunks are analysed; a non-final update holds back `total_lookahead` features; when no sample is
+        // new the encoder does not run at all.  The GPU then encodes the analysed audio in one pass and
+        // uses the first `emitted` features as memory, which equals the reference's chunk-by-chunk state.
+        const size_t L = s.size();
+        if (s.stream_processed < L) {
+          s.stream_processed += (L - s.stream_processed) / 1280 * 1280;
+          const int n = (int)(s.stream_processed / 320);
+          const int stable = s.is_complete ? n : std::max(0, n - model_->dims().lookahead());
+          if (n > 0 && stable > s.stream_emitted) s.stream_emitted = stable;
+        }
+        p.line.has_text = true;  // the streaming path always returns a string (possibly empty)
+        if (s.stream_emitted > 0 && (s.is_complete || options_.decode_incomplete_lines)) {
+          p.run = true;
+          ptrs.push_back(s.data());
+          lens.push_back(s.stream_processed);
+          plan_emitted.push_back(s.stream_emitted);
+          int budget;
+          if (options_.use_speculative_decoding && s.stream_decoded) {
+            // decode_full (moonshine-streaming-model.cpp:1217-1219): verify-then-continue returns what greedy
+            // returns, but budgets by memory length and leaves EOS out
+            const float dur = (float)s.stream_emitted * 0.020f;
+            budget = std::min((int)std::ceil((double)dur * 6.5), model_->dims().max_seq_len);
+            p.strip_eos = true;
+          } else {
+            const float dur = (float)L / (float)kSampleRate;
+            budget = std::min((int)std::ceil(dur * options_.max_tokens_per_second), 256);
+          }
+          plan_max_tokens.push_back(budget);
+          s.stream_decoded = true;
+        }
+      } else if (model_) {
         if (!s.is_complete && !options_.decode_incomplete_lines) {
           p.line.has_text = true;  // empty string, like the reference
         } else {
@@ -374,7 +416,11 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
   if (!ptrs.empty()) {
     std::lock_guard<std::mutex> lock(model_mutex_);
     const auto t0 = std::chrono::steady_clock::now();
-    model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens);
+    StreamPlan plan;
+    plan.emitted = plan_emitted.data();
+    plan.max_tokens = plan_max_tokens.data();
+    model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens,
+                       nullptr, streaming ? &plan : nullptr);
     latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                      std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("MOONSHINE_B200_HOST_PROF"))
@@ -385,7 +431,9 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
   for (Pending& p : pend) {
     Segment& s = (*jobs[p.job].segments)[p.seg];
     if (p.run) {
-      const std::string text = tokenizer_->tokens_to_text(tokens[ti++]);
+      std::vector<int32_t>& ids = tokens[ti++];
+      if (p.strip_eos && !ids.empty() && ids.back() == model_->dims().eos) ids.pop_back();
+      const std::string text = tokenizer_->tokens_to_text(ids);
       if (options_.log_output_text) MSB_LOGF("Transcribed text: '%s'", text.c_str());
       p.line.text = sanitize_utf8(text);
       p.line.has_text = true;

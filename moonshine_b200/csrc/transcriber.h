@@ -32,6 +32,7 @@ struct TranscriberOptions {
   bool log_output_text = false;
   bool word_timestamps = false;
   bool identify_speakers = false;
+  bool use_speculative_decoding = true;  // streaming archs: decides the token budget rule, see update_outputs
   std::vector<std::string> keyterms;
   std::string context;
   int device = -1;  // additive option "device": CUDA ordinal (-1 = current / LOCAL_RANK)
@@ -49,6 +50,12 @@ struct Segment {
   float end_time = 0.f;
   bool is_complete = false;
   bool just_updated = false;
+  // streaming architectures: per-segment state of Transcriber::transcribe_segment_with_streaming_model
+  // (core/transcriber.cpp:1321-1372) -- samples analysed so far (whole 1280-sample chunks), encoder
+  // features released to the decoder, and whether this segment was decoded before.
+  size_t stream_processed = 0;
+  int stream_emitted = 0;
+  bool stream_decoded = false;
 };
 
 // The reference's VoiceActivityDetector (core/voice-activity-detector.cpp)
