@@ -94,6 +94,8 @@ ARCHS = {
 
 
 def dims_for_arch(arch) -> ModelDims:
+    if isinstance(arch, ModelDims):
+        return arch
     if isinstance(arch, str):
         return ARCHS[arch]
     for d in ARCHS.values():

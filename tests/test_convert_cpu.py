@@ -44,3 +44,28 @@ def test_bf16_and_f16_tensors_are_widened(tmp_path):
     t = read_safetensors(str(p))
     np.testing.assert_array_equal(t["x"], a)
     np.testing.assert_array_equal(t["y"], a.reshape(2, 2))
+
+
+def test_streaming_checkpoint_with_config_json(tmp_path):
+    """HF MoonshineStreamingForConditionalGeneration layout: config.json carries the dimensions,
+    comp.log_k is a scalar, proj_out is a separate (untied) head."""
+    import json
+    from moonshine_b200.arch import ARCHS
+    d = ARCHS["test_streaming"]
+    w = synth_weights("test_streaming", 1, "scaled")
+    ck = {k: v for k, v in w.items() if k != "streaming.config"}
+    ck["model.encoder.embedder.comp.log_k"] = ck["model.encoder.embedder.comp.log_k"].reshape(())
+    write_safetensors(str(tmp_path / "model.safetensors"), ck)
+    cfg = {"model_type": "moonshine_streaming", "hidden_size": d.dim, "intermediate_size": d.ffn,
+           "num_hidden_layers": d.dec_layers, "num_attention_heads": d.heads, "vocab_size": d.vocab,
+           "max_position_embeddings": d.max_pos_emb, "tie_word_embeddings": False,
+           "rope_parameters": {"rope_type": "default", "rope_theta": 10000.0, "partial_rotary_factor": 0.8},
+           "encoder_config": {"hidden_size": d.enc_dim, "intermediate_size": d.enc_ffn,
+                              "num_hidden_layers": d.enc_layers, "sliding_windows": [list(x) for x in d.windows]}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    out = convert(str(tmp_path), str(tmp_path / "model_dir"), "tiny_streaming")
+    arch, got = read_msw(os.path.join(out, "model.msw"))
+    assert arch == 2
+    assert set(got) == set(w)
+    for k in w:
+        np.testing.assert_array_equal(got[k], w[k])
