@@ -94,6 +94,7 @@ def oracle_baseline(model, weights, audios, budget_s=20.0, max_utts=8):
     per-token decoder matmuls are tiny and 100+ spinning BLAS threads make the
     port slower, which would flatter the GPU."""
     from oracle.moonshine_oracle import Dims, Oracle
+    from oracle.moonshine_streaming_oracle import SDims, StreamingOracle
     try:
         from threadpoolctl import threadpool_limits
         ctx = threadpool_limits(limits=CPU_THREADS)
@@ -101,12 +102,14 @@ def oracle_baseline(model, weights, audios, budget_s=20.0, max_utts=8):
         import contextlib
         ctx = contextlib.nullcontext()
     with ctx:
-        o = Oracle(Dims.from_product(ARCHS[model]), weights)
+        streaming = ARCHS[model].streaming
+        o = (StreamingOracle(SDims.from_product(ARCHS[model]), weights) if streaming
+             else Oracle(Dims.from_product(ARCHS[model]), weights))
         t0 = time.perf_counter()
         n = 0
         toks = []
         for a in audios[:max_utts]:
-            tk, _, _ = o.greedy(a, keep_logits=False)
+            tk = (o.transcribe_segment(a, keep_logits=False) if streaming else o.greedy(a, keep_logits=False))[0]
             toks.append(tk)
             n += 1
             if time.perf_counter() - t0 > budget_s:
@@ -178,7 +181,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     model, B = args.model, args.batch
     d = ARCHS[model]
-    arch_enum = {"tiny": api.ModelArch.TINY, "base": api.ModelArch.BASE}[model]
+    arch_enum = {"tiny": api.ModelArch.TINY, "base": api.ModelArch.BASE,
+                 "tiny_streaming": api.ModelArch.TINY_STREAMING, "base_streaming": api.ModelArch.BASE_STREAMING}[model]
 
     # ---- weights: rank 0 builds the container, ONE NCCL broadcast replicates it ----
     from moonshine_b200.dist import broadcast_bytes
@@ -266,6 +270,8 @@ def main():
         ms_per_step = dev_total_ms / K
         # roofline of the dominant kernel (decoder step): algorithmic bytes / launch / measured time
         _, _, T = frontend_lengths(N_SAMPLES)
+        if d.streaming:
+            T = N_SAMPLES // 1280 * 4   # encoder features of the whole 1280-sample chunks (20 ms each)
         steps_run = int(tm["decode_steps"])
         bytes_per_launch = float(np.mean([decoder_step_bytes(d, B, T, s) for s in range(steps_run)]))
         launch_ms = float(np.mean(dec_ms)) / max(steps_run, 1)
@@ -282,8 +288,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "rtf": (dev_total_ms / 1000.0) / (utts * 10.0),
             "config": {
-                "workload": f"moonshine-{model}, batch={B} synthetic 10s@16kHz utterances per GPU, conv frontend + "
-                            f"encoder + greedy decoder ({steps_run} decode steps; seeded random weights never emit EOS)",
+                "workload": f"moonshine-{model}, batch={B} synthetic 10s@16kHz utterances per GPU, "
+                            + ("streaming frontend + sliding-window encoder + adapter" if d.streaming else "conv frontend + encoder")
+                            + f" + greedy decoder ({steps_run} decode steps; seeded random weights never emit EOS)",
                 "batch_per_gpu": B, "global_batch": B * world, "audio_seconds_per_utt": 10.0,
                 "weights": "seeded synthetic (HF init std 0.02), fp32 storage; cross K/V cache fp16",
                 "parallelism": f"dp{world} (utterance shards, one NCCL weight broadcast at init)",

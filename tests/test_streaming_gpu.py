@@ -31,25 +31,32 @@ def soracle(arch, seed=0, init="scaled"):
     return StreamingOracle(SDims.from_product(ARCHS[arch]), synth_weights(arch, seed, init))
 
 
-def check_stream_case(arch, seed, init, audios, final=True):
+def check_stream_case(arch, seed, init, audios, final=True, only=None):
+    """`only`: indices compared with the oracle (the rest of the batch is teacher-forced with
+    utterance only[0]'s ids and just has to run) -- keeps full-size batches affordable on the CPU side."""
     d = ARCHS[arch]
     o = soracle(arch, seed, init)
-    refs = [o.transcribe_segment(a, is_final=final) for a in audios]
-    max_steps = max(len(r[0]) - 1 for r in refs)
+    idx = list(range(len(audios))) if only is None else list(only)
+    ref_by = {i: o.transcribe_segment(audios[i], is_final=final) for i in idx}
+    refs = [ref_by.get(i) for i in range(len(audios))]
+    max_steps = max(len(r[0]) - 1 for r in ref_by.values())
     forced = np.zeros((len(audios), max_steps + 2), np.int32)
-    for i, (toks, _, _) in enumerate(refs):
+    for i in range(len(audios)):
+        toks = (refs[i] or ref_by[idx[0]])[0]
         forced[i, :len(toks)] = toks
     t = make_transcriber(arch, seed, init)
     t.debug_stream_partial(not final)
     mems, logits, _ = t.debug_run(audios, d.dim, d.vocab, forced=forced, logits_steps=max_steps, max_tokens=300)
-    for i, (toks, ref_logits, ref_mem) in enumerate(refs):
+    for i in idx:
+        toks, ref_logits, ref_mem = refs[i]
         assert mems[i].shape == ref_mem.shape, f"memory shape utt {i}"
         assert rel_err(mems[i], ref_mem) < TOL, f"memory utt {i}"
         for s in range(len(toks) - 1):
             e = np.abs(logits[s, i] - ref_logits[s]).max() / np.abs(ref_logits[s]).max()
             assert e < TOL, f"logits utt {i} step {s}: {e}"
     _, _, toks_gpu = t.debug_run(audios, d.dim, d.vocab, want_encoder=False, max_tokens=300)
-    for i, (toks, ref_logits, _) in enumerate(refs):
+    for i in idx:
+        toks, ref_logits, _ = refs[i]
         srt = np.sort(ref_logits, axis=1)
         margin = (srt[:, -1] - srt[:, -2]) / np.abs(ref_logits).max(1)
         got = toks_gpu[i]
@@ -86,6 +93,13 @@ def test_tiny_streaming():
 
 def test_base_streaming():
     check_stream_case("base_streaming", 1, "scaled", [synth_audio(1, 32011), synth_audio(2, 70000)])
+
+
+def test_config4_base_streaming_batch64_full_size():
+    """BASELINE config #4: moonshine-base streaming, batch 64, 10 s clips (500 features, 65 tokens each);
+    first / middle / last utterance against the oracle."""
+    audios = [synth_audio(i) for i in range(64)]
+    check_stream_case("base_streaming", 0, "scaled", audios, only=[0, 31, 63])
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "hfs_*.npz"))),
