@@ -83,6 +83,29 @@ void launch_softmax_rows(float* S, const int64_t* offS, const int* Mz, const int
                          int groups, int max_m, cudaStream_t stream, int win_past = -1, int win_future = 0);
 
 // ---------------------------------------------------------------------------
+// Fused encoder self-attention (attention_tc.cu): per group z = (utterance, head)
+//   out_z[m, 0:hd] = softmax_k(scale * Q_z[m] . K_z[k]) V_z[k]      m, k < T_z
+// Q_z / K_z rows live in one array with row stride ldqk, V_z is given transposed ([hd][ldv], keys contiguous).
+// win_past >= 0 restricts query m to keys m - win_past .. m + win_future (inclusive).
+// ---------------------------------------------------------------------------
+struct AttnParams {
+  const float* qk = nullptr;
+  const float* vt = nullptr;
+  float* out = nullptr;
+  const int64_t* offQ = nullptr;
+  const int64_t* offK = nullptr;
+  const int64_t* offV = nullptr;
+  const int64_t* offO = nullptr;
+  const int* Tz = nullptr;
+  int ldqk = 0, ldv = 0, ldo = 0, hd = 0;
+  float scale = 1.0f;
+  int win_past = -1, win_future = 0;
+};
+// true when every query tile's key range fits the kernel's TMEM budget (448 score columns)
+bool attention_tc_supported(int max_t, int hd, int win_past, int win_future);
+void launch_attention_tc(const AttnParams& p, int groups, int max_t, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
 // Streaming frontend / adapter
 // ---------------------------------------------------------------------------
 // Per 80-sample frame: CMVN ((x - mean) / sqrt(mean((x - mean)^2) + 1e-6)), then asinh(k * x).

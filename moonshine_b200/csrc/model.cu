@@ -618,7 +618,13 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   reserve_zero(ln_, (size_t)tot3 * E);
   reserve_zero(qk_, (size_t)tot3 * 2 * E);
   reserve_zero(vt_, (size_t)B * E * Tp);
-  reserve_zero(scores_, (size_t)BH * maxT3 * Tp);
+  {
+    // only the unfused attention path materialises scores in HBM
+    bool need_scores = std::getenv("MOONSHINE_B200_ATTN") != nullptr;
+    for (int l = 0; l < d_.enc_layers; l++)
+      need_scores = need_scores || !attention_tc_supported(maxT3, ehd, S ? d_.win_past[l] : -1, S ? d_.win_future[l] : 0);
+    if (need_scores) reserve_zero(scores_, (size_t)BH * maxT3 * Tp);
+  }
   reserve_zero(attn_, (size_t)tot3 * E);
   reserve_zero(mid_, (size_t)tot3 * EI);
   reserve_zero(enc_out_, (size_t)tot3 * std::max(D, E));
@@ -681,6 +687,10 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
 
   // ---------------- encoder layers ----------------
   const float scale = 1.0f / std::sqrt((float)ehd);
+  static const bool fused_attn = [] {
+    const char* e = std::getenv("MOONSHINE_B200_ATTN");
+    return !(e && std::string(e) == "unfused");
+  }();
   for (int l = 0; l < d_.enc_layers; l++) {
     const EncLayer& w = enc_[l];
     launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, E, stream_);
@@ -701,22 +711,33 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       g.groups = B; g.M = E; g.N = maxT3; g.K = E; g.Nz = d_t3;
       launch_gemm(g, stream_);
     }
-    {  // S_z = scale * Q_z K_z^T
-      GemmParams g;
-      g.A = qk_.ptr; g.lda = 2 * E; g.offA = d_offq; g.W = qk_.ptr; g.ldw = 2 * E; g.offW = d_offk;
-      g.C = scores_.ptr; g.offC = d_offs; g.rs = Tp;
-      g.groups = BH; g.M = maxT3; g.N = maxT3; g.K = ehd; g.Mz = d_mzt; g.Nz = d_mzt;
-      g.alpha = scale;
-      launch_gemm(g, stream_);
-    }
-    if (S) launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_, d_.win_past[l], d_.win_future[l]);
-    else launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_);
-    {  // O_z = P_z V_z
-      GemmParams g;
-      g.A = scores_.ptr; g.lda = Tp; g.offA = d_offs; g.W = vt_.ptr; g.ldw = Tp; g.offW = d_offvh;
-      g.C = attn_.ptr; g.offC = d_offo; g.rs = E;
-      g.groups = BH; g.M = maxT3; g.N = ehd; g.K = maxT3; g.Mz = d_mzt; g.Kz = d_mzt;
-      launch_gemm(g, stream_);
+    const int wp = S ? d_.win_past[l] : -1, wf = S ? d_.win_future[l] : 0;
+    if (fused_attn && attention_tc_supported(maxT3, ehd, wp, wf)) {
+      // softmax(scale * Q K^T [window]) V in one tcgen05 kernel; scores stay in TMEM
+      AttnParams a;
+      a.qk = qk_.ptr; a.vt = vt_.ptr; a.out = attn_.ptr;
+      a.offQ = d_offq; a.offK = d_offk; a.offV = d_offvh; a.offO = d_offo; a.Tz = d_mzt;
+      a.ldqk = 2 * E; a.ldv = Tp; a.ldo = E; a.hd = ehd; a.scale = scale; a.win_past = wp; a.win_future = wf;
+      launch_attention_tc(a, BH, maxT3, stream_);
+      launches -= 2;
+    } else {
+      {  // S_z = scale * Q_z K_z^T
+        GemmParams g;
+        g.A = qk_.ptr; g.lda = 2 * E; g.offA = d_offq; g.W = qk_.ptr; g.ldw = 2 * E; g.offW = d_offk;
+        g.C = scores_.ptr; g.offC = d_offs; g.rs = Tp;
+        g.groups = BH; g.M = maxT3; g.N = maxT3; g.K = ehd; g.Mz = d_mzt; g.Nz = d_mzt;
+        g.alpha = scale;
+        launch_gemm(g, stream_);
+      }
+      if (S) launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_, d_.win_past[l], d_.win_future[l]);
+      else launch_softmax_rows(scores_.ptr, d_offs, d_mzt, d_mzt, Tp, BH, maxT3, stream_);
+      {  // O_z = P_z V_z
+        GemmParams g;
+        g.A = scores_.ptr; g.lda = Tp; g.offA = d_offs; g.W = vt_.ptr; g.ldw = Tp; g.offW = d_offvh;
+        g.C = attn_.ptr; g.offC = d_offo; g.rs = E;
+        g.groups = BH; g.M = maxT3; g.N = ehd; g.K = maxT3; g.Mz = d_mzt; g.Kz = d_mzt;
+        launch_gemm(g, stream_);
+      }
     }
     {  // x += attn Wo^T
       GemmParams g;
