@@ -235,6 +235,14 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_run(
    moonshine_b200_transcribe_device treat each utterance as a NON-final update of its segment
    (the encoder's look-ahead features are held back, core/moonshine-streaming-model.cpp:624-626). */
 MOONSHINE_EXPORT int32_t moonshine_b200_debug_stream_partial(int32_t transcriber_handle, int32_t enabled);
+/* Host-only parity hooks (no GPU): this library's detokeniser (reference: BinTokenizer::tokens_to_text,
+   core/bin-tokenizer/bin-tokenizer.cpp:406-425) and resampler (core/resampler.cpp:5-86), so CPU tests can
+   compare them with the reference's own compiled sources (oracle/_ref).  Return the full output length. */
+MOONSHINE_EXPORT int64_t moonshine_b200_debug_tokens_to_text(const uint8_t *tokenizer, uint64_t tokenizer_size,
+                                                             const int32_t *ids, int32_t n, char *out,
+                                                             int64_t cap);
+MOONSHINE_EXPORT int64_t moonshine_b200_debug_resample(const float *in, int64_t n, float in_rate,
+                                                       float out_rate, float *out, int64_t cap);
 /* Standalone grouped-GEMM hook used by the kernel unit tests (device pointers). */
 MOONSHINE_EXPORT int32_t moonshine_b200_test_gemm(const float *dA, const float *dW, float *dC,
                                                   int32_t M, int32_t N, int32_t K, int32_t lda,

@@ -432,6 +432,35 @@ int32_t moonshine_b200_debug_run(int32_t transcriber_handle, const float* const*
   return MOONSHINE_ERROR_NONE;
 }
 
+// ---- host-only parity hooks (no GPU needed): the product's own helpers, callable from the CPU tests that
+// compare them with the reference's compiled sources (oracle/_ref) ----
+int64_t moonshine_b200_debug_tokens_to_text(const uint8_t* tokenizer, uint64_t tokenizer_size, const int32_t* ids,
+                                            int32_t n, char* out, int64_t cap) {
+  try {
+    Tokenizer tk(tokenizer, (size_t)tokenizer_size);
+    const std::string s = tk.tokens_to_text(std::vector<int32_t>(ids, ids + n));
+    const int64_t m = std::min<int64_t>((int64_t)s.size(), cap);
+    if (out && m > 0) std::memcpy(out, s.data(), (size_t)m);
+    return (int64_t)s.size();
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_tokens_to_text failed: %s", e.what());
+    return -1;
+  }
+}
+
+int64_t moonshine_b200_debug_resample(const float* in, int64_t n, float in_rate, float out_rate, float* out,
+                                      int64_t cap) {
+  try {
+    const std::vector<float> r = resample_audio(in, (size_t)n, in_rate, out_rate);
+    const int64_t m = std::min<int64_t>((int64_t)r.size(), cap);
+    if (out && m > 0) std::memcpy(out, r.data(), (size_t)m * sizeof(float));
+    return (int64_t)r.size();
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_resample failed: %s", e.what());
+    return -1;
+  }
+}
+
 int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, int32_t M, int32_t N,
                                  int32_t K, int32_t lda, int32_t ldw, int32_t ldc, const float* d_bias,
                                  int32_t act, int32_t accumulate, int32_t impl) {

@@ -1,0 +1,94 @@
+"""CPU: this repo's host-side helpers against the REFERENCE's own code, compiled from /root/reference into
+oracle/_ref/libmoonshine_ref_helpers.so by oracle/build_ref.py (the library travels to the GPU box; the
+sources do not).  Covers the detokeniser and the resampler: product C++ == oracle numpy == reference C++."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from moonshine_b200 import api
+from moonshine_b200.weights import synth_tokenizer_bin
+from oracle import build_ref
+from oracle import moonshine_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def ref():
+    path = build_ref.build()
+    if path is None or not os.path.exists(path):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    lib.ref_tokenizer_new.restype = c.c_void_p
+    lib.ref_tokenizer_new.argtypes = [c.c_char_p, c.c_uint64]
+    lib.ref_tokenizer_free.argtypes = [c.c_void_p]
+    lib.ref_tokens_to_text.restype = c.c_int64
+    lib.ref_tokens_to_text.argtypes = [c.c_void_p, c.POINTER(c.c_int32), c.c_int32, c.c_char_p, c.c_int64]
+    lib.ref_resample.restype = c.c_int64
+    lib.ref_resample.argtypes = [c.POINTER(c.c_float), c.c_int64, c.c_float, c.c_float, c.POINTER(c.c_float),
+                                 c.c_int64]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def product():
+    return api.load_library()
+
+
+def _i32(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _f32(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def test_detokeniser_matches_reference_code(ref, product):
+    vocab_n = 2000
+    tok = synth_tokenizer_bin(vocab_n)
+    # add pieces the synthetic table lacks: multi-byte UTF-8, embedded markers, angle-bracket lookalikes
+    extra = ["▁héllo", "wörld▁", "<x>", "<>", "a<b>", "▁", "▁▁two", " lead", "trail ", "日本語"]
+    blob = bytearray(tok)
+    for e in extra:
+        b = e.encode("utf-8")
+        blob.append(len(b))
+        blob += b
+    blob = bytes(blob)
+    n_vocab = vocab_n + len(extra)
+    vocab = orc.load_tokenizer_bin(blob)
+    assert len(vocab) == n_vocab
+    h = ref.ref_tokenizer_new(blob, len(blob))
+    assert h
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(0, 40))
+        ids = rng.integers(0, n_vocab, n).astype(np.int32)
+        if trial % 3 == 0 and n:
+            ids[rng.integers(0, n, max(1, n // 4))] = rng.integers(vocab_n, n_vocab, max(1, n // 4))
+        if trial % 5 == 0 and n:
+            ids[0] = 1
+            ids[-1] = 2
+        buf_r = ctypes.create_string_buffer(4096)
+        buf_p = ctypes.create_string_buffer(4096)
+        nr = ref.ref_tokens_to_text(h, _i32(ids), n, buf_r, 4096)
+        npd = product.moonshine_b200_debug_tokens_to_text(blob, len(blob), _i32(ids), n, buf_p, 4096)
+        want = buf_r.raw[:nr]
+        assert nr >= 0 and npd == nr and buf_p.raw[:npd] == want
+        assert orc.tokens_to_text(vocab, ids.tolist()) == want
+    ref.ref_tokenizer_free(h)
+
+
+@pytest.mark.parametrize("rate", [8000, 11025, 22050, 32000, 44100, 48000, 16000])
+def test_resampler_matches_reference_code(ref, product, rate):
+    rng = np.random.default_rng(rate)
+    for n in (1, 2, 17, 1000, 44100 // 3 + 5):
+        x = (rng.standard_normal(n) * 0.3).astype(np.float32)
+        cap = n * 3 + 16
+        out_r = np.zeros(cap, np.float32)
+        out_p = np.zeros(cap, np.float32)
+        nr = ref.ref_resample(_f32(x), n, float(rate), 16000.0, _f32(out_r), cap)
+        npd = product.moonshine_b200_debug_resample(_f32(x), n, float(rate), 16000.0, _f32(out_p), cap)
+        assert nr == npd
+        np.testing.assert_array_equal(out_p[:npd], out_r[:nr])
+        np.testing.assert_array_equal(orc.resample_audio(x, rate), out_r[:nr])
