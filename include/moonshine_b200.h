@@ -241,6 +241,12 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_stream_partial(int32_t transcriber
 MOONSHINE_EXPORT int64_t moonshine_b200_debug_tokens_to_text(const uint8_t *tokenizer, uint64_t tokenizer_size,
                                                              const int32_t *ids, int32_t n, char *out,
                                                              int64_t cap);
+/* Word alignment (reference: align_words, core/word-alignment.cpp:181-394) on caller-supplied cross-attention
+   [heads_total][steps][frames]; word texts are written NUL-separated.  Returns the word count. */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_align_words(
+    const uint8_t *tokenizer, uint64_t tokenizer_size, const float *xattn, int32_t heads_total, int32_t steps,
+    int32_t frames, const int32_t *tokens, int32_t n_tokens, float time_per_frame, float *starts, float *ends,
+    char *text_out, int64_t text_cap, int32_t max_words);
 MOONSHINE_EXPORT int64_t moonshine_b200_debug_resample(const float *in, int64_t n, float in_rate,
                                                        float out_rate, float *out, int64_t cap);
 /* Standalone grouped-GEMM hook used by the kernel unit tests (device pointers). */

@@ -11,6 +11,7 @@
 
 #include "../../include/moonshine_b200.h"
 #include "transcriber.h"
+#include "word_alignment.h"
 
 using namespace msb;
 
@@ -444,6 +445,31 @@ int64_t moonshine_b200_debug_tokens_to_text(const uint8_t* tokenizer, uint64_t t
     return (int64_t)s.size();
   } catch (const std::exception& e) {
     MSB_LOGF("debug_tokens_to_text failed: %s", e.what());
+    return -1;
+  }
+}
+
+int32_t moonshine_b200_debug_align_words(const uint8_t* tokenizer, uint64_t tokenizer_size, const float* xattn,
+                                         int32_t heads_total, int32_t steps, int32_t frames, const int32_t* tokens,
+                                         int32_t n_tokens, float time_per_frame, float* starts, float* ends,
+                                         char* text_out, int64_t text_cap, int32_t max_words) {
+  try {
+    Tokenizer tk(tokenizer, (size_t)tokenizer_size);
+    const std::vector<WordTiming> w = align_words(xattn, heads_total, steps, frames,
+                                                  std::vector<int32_t>(tokens, tokens + n_tokens), time_per_frame, tk);
+    int64_t o = 0;
+    for (int32_t i = 0; i < (int32_t)w.size() && i < max_words; i++) {
+      starts[i] = w[i].start;
+      ends[i] = w[i].end;
+      if (o + (int64_t)w[i].text.size() + 1 <= text_cap) {
+        std::memcpy(text_out + o, w[i].text.data(), w[i].text.size());
+        o += (int64_t)w[i].text.size();
+        text_out[o++] = 0;
+      }
+    }
+    return (int32_t)w.size();
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_align_words failed: %s", e.what());
     return -1;
   }
 }

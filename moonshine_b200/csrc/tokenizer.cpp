@@ -66,6 +66,12 @@ std::string Tokenizer::tokens_to_text(const std::vector<int32_t>& tokens, bool s
   return out.substr(b, e - b);
 }
 
+bool Tokenizer::starts_word(int32_t token) const {
+  if (token < 0 || (size_t)token >= pieces_.size()) return false;
+  const std::string& p = pieces_[(size_t)token];
+  return p.size() >= 3 && (uint8_t)p[0] == 0xE2 && (uint8_t)p[1] == 0x96 && (uint8_t)p[2] == 0x81;
+}
+
 std::string sanitize_utf8(const std::string& s) {
   std::string out;
   out.reserve(s.size());

@@ -16,6 +16,8 @@ class Tokenizer {
   // Throws std::out_of_range / std::runtime_error like the reference's
   // `.at(token)` and empty-token check.
   std::string tokens_to_text(const std::vector<int32_t>& tokens, bool skip_specials = true) const;
+  // piece begins with the word-boundary marker U+2581 (core/word-alignment.cpp:158-170); false for bad ids
+  bool starts_word(int32_t token) const;
 
  private:
   std::vector<std::string> pieces_;

@@ -92,3 +92,49 @@ def test_resampler_matches_reference_code(ref, product, rate):
         assert nr == npd
         np.testing.assert_array_equal(out_p[:npd], out_r[:nr])
         np.testing.assert_array_equal(orc.resample_audio(x, rate), out_r[:nr])
+
+
+def test_word_alignment_matches_reference_code(ref, product):
+    """align_words (core/word-alignment.cpp): z-score, width-7 median, head mean, DTW, word grouping, overlap
+    fix -- this library's implementation against the reference's compiled one, on random and on peaked
+    (speech-like, monotonic) attention maps."""
+    c = ctypes
+    ref.ref_align_words.restype = c.c_int32
+    ref.ref_align_words.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+                                    c.POINTER(c.c_int32), c.c_int32, c.c_float, c.POINTER(c.c_float),
+                                    c.POINTER(c.c_float), c.c_char_p, c.c_int64, c.c_int32]
+    vocab_n = 600
+    blob = synth_tokenizer_bin(vocab_n)
+    h = ref.ref_tokenizer_new(blob, len(blob))
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        layers, heads = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+        steps = int(rng.integers(1, 24))
+        frames = int(rng.integers(1, 90)) if trial % 4 else int(rng.integers(1, 6))
+        x = rng.random((layers * heads, steps, frames)).astype(np.float32)
+        if trial % 2:  # monotonic ridge + noise, softmax-normalised like real cross-attention
+            centre = np.linspace(0, frames - 1, steps)[None, :, None]
+            x = np.exp(-0.5 * ((np.arange(frames)[None, None, :] - centre) / 2.0) ** 2) * 4 + x
+            x = (np.exp(x) / np.exp(x).sum(-1, keepdims=True)).astype(np.float32)
+        n_tok = steps + 1 if trial % 3 else steps  # with / without a final EOS row
+        toks = np.concatenate([[1], rng.integers(3, vocab_n, n_tok - 1)]).astype(np.int32)
+        if trial % 3:
+            toks[-1] = 2
+        tpf = np.float32(10.0 / frames)
+        outs = []
+        for fn, first in ((ref.ref_align_words, (h,)), (product.moonshine_b200_debug_align_words, (blob, len(blob)))):
+            st, en = np.zeros(64, np.float32), np.zeros(64, np.float32)
+            txt = ctypes.create_string_buffer(8192)
+            if fn is ref.ref_align_words:
+                n = fn(*first, _f32(x), layers, heads, steps, frames, _i32(toks), len(toks), tpf, _f32(st), _f32(en),
+                       txt, 8192, 64)
+            else:
+                n = fn(*first, _f32(x), layers * heads, steps, frames, _i32(toks), len(toks), tpf, _f32(st), _f32(en),
+                       txt, 8192, 64)
+            words = txt.raw.split(b"\0")[:max(n, 0)]
+            outs.append((n, st[:max(n, 0)].copy(), en[:max(n, 0)].copy(), words))
+        (nr, sr, er, wr), (npd, sp, ep, wp) = outs
+        assert nr == npd and wr == wp
+        np.testing.assert_array_equal(sp, sr)
+        np.testing.assert_array_equal(ep, er)
+    ref.ref_tokenizer_free(h)
