@@ -203,6 +203,15 @@ def _check(code: int, what: str):
 
 
 @dataclass
+class WordTiming:
+    """Mirror of the reference binding's word record (moonshine_voice/transcriber.py)."""
+    word: str
+    start: float
+    end: float
+    confidence: float = 1.0
+
+
+@dataclass
 class TranscriptLine:
     text: Optional[str]
     start_time: float
@@ -214,6 +223,7 @@ class TranscriptLine:
     has_text_changed: bool = False
     audio_data: Optional[np.ndarray] = None
     last_transcription_latency_ms: int = 0
+    words: Optional[List[WordTiming]] = None
 
 
 @dataclass
@@ -251,7 +261,9 @@ def _parse_transcript(tc: TranscriptC) -> Transcript:
             start_time=l.start_time, duration=l.duration, line_id=l.id,
             is_complete=bool(l.is_complete), is_updated=bool(l.is_updated), is_new=bool(l.is_new),
             has_text_changed=bool(l.has_text_changed), audio_data=audio,
-            last_transcription_latency_ms=l.last_transcription_latency_ms))
+            last_transcription_latency_ms=l.last_transcription_latency_ms,
+            words=[WordTiming(l.words[k].text.decode("utf-8", errors="replace"), l.words[k].start, l.words[k].end,
+                              l.words[k].confidence) for k in range(l.word_count)] if l.words and l.word_count else None))
     return out
 
 

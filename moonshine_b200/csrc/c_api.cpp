@@ -74,9 +74,6 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else throw std::runtime_error("Unknown transcriber option: '" + name + "', value=" + value);
   }
   if (out.identify_speakers) throw std::runtime_error("identify_speakers is not supported by moonshine-b200");
-  if (out.word_timestamps) {
-    MSB_LOGF("word_timestamps is accepted but not produced by moonshine-b200 yet (words stay NULL)");
-  }
 }
 
 int32_t register_transcriber(Transcriber* t) {

@@ -748,6 +748,11 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
 #pragma unroll
     for (int i = 0; i < kWarpsC; i++) tot += red_sum[i];
     const float inv = 1.0f / tot;
+    if (p.xattn_out != nullptr && t4 < Tpad) {  // word timestamps: export this (utterance, layer, head, step) row
+      float* dst = p.xattn_out +
+                   (((((int64_t)(b0 + b) * p.L + l) * H + h) * p.xattn_steps + p.step) * Tpad + t4);
+      *reinterpret_cast<float4*>(dst) = make_float4(s0 * inv, s1 * inv, s2 * inv, s3 * inv);
+    }
     // ---- PV over V chunks (rows = time); thread (g, dq) owns 4 dims of rows g, g+G, ... ----
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const int g = threadIdx.x / tpr, dq = threadIdx.x - g * tpr;

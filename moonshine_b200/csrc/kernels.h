@@ -173,6 +173,8 @@ struct DecoderParams {
   int* n_active;          // [1] utterances still decoding (updated at step start)
   float* logits_out;      // optional [B][V] dump of this step's logits (parity/debug)
   const int* forced;      // optional [B][Smax + 1] teacher-forced ids
+  float* xattn_out;       // optional [B][L][H][xattn_steps][Tpad] cross-attention probabilities (word timestamps)
+  int xattn_steps;
   unsigned int* barrier;  // [2] grid barrier state
 };
 void launch_decoder_step(const DecoderParams& p, int grid, cudaStream_t stream);

@@ -395,7 +395,8 @@ const StreamPlan* Model::auto_plan(const uint64_t*& n_samples, int B, float max_
 }
 
 void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B, float max_tps,
-                       std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan) {
+                       std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
+                       std::vector<CrossAttention>* xattn) {
   CUDA_CHECK(cudaSetDevice(device_));
   tokens.clear();
   if (B <= 0) return;
@@ -439,7 +440,7 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
     }
   }
   const auto t1 = std::chrono::steady_clock::now();
-  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg, plan);
+  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg, plan, xattn);
   if (std::getenv("MOONSHINE_B200_HOST_PROF")) {
     const auto t2 = std::chrono::steady_clock::now();
     MSB_LOGF("host profile: staging memcpy %.2f ms, h2d+run %.2f ms",
@@ -460,7 +461,8 @@ void Model::transcribe_device(const float* d_pcm, int64_t stride, const uint64_t
 }
 
 void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
-                std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan) {
+                std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
+                std::vector<CrossAttention>* xattn) {
   const int D = d_.dim, I = d_.ffn, H = d_.heads, hd = d_.head_dim, V = d_.vocab;
   const int L = d_.dec_layers;
   times_ = StageTimes();
@@ -878,6 +880,8 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     CUDA_CHECK(cudaMemsetAsync(logits_dbg_.ptr, 0, (size_t)dbg_steps * B * V * sizeof(float), stream_));
   }
   const int grid = sm_count_;
+  p.xattn_out = nullptr;
+  p.xattn_steps = 0;
   // v2 streams operands through the smem ring; its cross-attention maps one thread to 4 key
   // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
   const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 32 == 0;
@@ -886,6 +890,16 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   if (prof_step >= 0) {
     prof_buf.reserve((size_t)grid * 512);
     CUDA_CHECK(cudaMemsetAsync(prof_buf.ptr, 0, prof_buf.bytes(), stream_));
+  }
+  if (xattn != nullptr) {
+    xattn->clear();
+    if (use_v2) {  // the export lives in the v2 step kernel
+      p.xattn_steps = std::max(max_steps, 1);
+      const size_t n = (size_t)B * L * H * p.xattn_steps * Tpad;
+      xattn_dev_.reserve(n);
+      CUDA_CHECK(cudaMemsetAsync(xattn_dev_.ptr, 0, n * sizeof(float), stream_));
+      p.xattn_out = xattn_dev_.ptr;
+    }
   }
   for (int t = 0; t < max_steps; t++) {
     p.step = t;
@@ -925,6 +939,26 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   for (int b = 0; b < B; b++) {
     const int n = std::min(hn[b], Smax + 1);
     tokens[b].assign(ht + (size_t)b * (Smax + 1), ht + (size_t)b * (Smax + 1) + n);
+  }
+  if (xattn != nullptr && p.xattn_out != nullptr) {
+    // [B][L][H][S][Tpad] on the device -> per utterance [L * H][steps_b][T_b]
+    const size_t per_utt = (size_t)L * H * p.xattn_steps * Tpad;
+    std::vector<float> host(per_utt);
+    xattn->resize(B);
+    for (int b = 0; b < B; b++) {
+      CrossAttention& xa = (*xattn)[b];
+      xa.heads_total = L * H;
+      xa.steps = std::max((int)tokens[b].size() - 1, 0);
+      xa.frames = Tm[b];
+      xa.prob.assign((size_t)xa.heads_total * xa.steps * xa.frames, 0.f);
+      if (xa.steps == 0) continue;
+      CUDA_CHECK(cudaMemcpy(host.data(), xattn_dev_.ptr + (size_t)b * per_utt, per_utt * sizeof(float),
+                            cudaMemcpyDeviceToHost));
+      for (int lh = 0; lh < xa.heads_total; lh++)
+        for (int s2 = 0; s2 < xa.steps; s2++)
+          std::memcpy(&xa.prob[((size_t)lh * xa.steps + s2) * xa.frames],
+                      &host[((size_t)lh * p.xattn_steps + s2) * Tpad], (size_t)xa.frames * sizeof(float));
+    }
   }
   if (dbg && dbg->logits && dbg_steps > 0) {
     dbg->logits->resize((size_t)dbg_steps * B * V);

@@ -34,6 +34,13 @@ struct StreamPlan {
   const int* max_tokens = nullptr;  // [B] decode budget
 };
 
+// Decoder cross-attention of one utterance, as align_words consumes it: [layers * heads][steps][frames]
+// (layer-major), steps = decoder runs = generated ids, frames = encoder memory length.
+struct CrossAttention {
+  int heads_total = 0, steps = 0, frames = 0;
+  std::vector<float> prob;
+};
+
 struct StageTimes {
   float frontend_ms = 0, encoder_ms = 0, cross_kv_ms = 0, decode_ms = 0;
   int decode_steps = 0;
@@ -53,7 +60,8 @@ class Model {
   // Host PCM (16 kHz mono float).  Copies to the device inside the call.
   void transcribe(const float* const* pcm, const uint64_t* n_samples, int B,
                   float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
-                  DebugCapture* dbg = nullptr, const StreamPlan* plan = nullptr);
+                  DebugCapture* dbg = nullptr, const StreamPlan* plan = nullptr,
+                  std::vector<CrossAttention>* xattn = nullptr);
   // Device-resident PCM: row b at d_pcm + b * stride.
   void transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
                          float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
@@ -86,7 +94,8 @@ class Model {
   // plan-less call on a streaming model: one-shot bookkeeping per utterance
   const StreamPlan* auto_plan(const uint64_t*& n_samples, int B, float max_tps, AutoPlan& ap) const;
   void run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
-           std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan);
+           std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
+           std::vector<CrossAttention>* xattn = nullptr);
 
   Dims d_;
   int device_ = 0;
@@ -121,7 +130,7 @@ class Model {
   DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_, frames_;
   DeviceBuffer<double> gn_partial_;
   DeviceBuffer<__half> kc_, vc_;
-  DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_;
+  DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_, xattn_dev_;
   DeviceBuffer<int> cand_idx_, tokens_dev_, ntok_dev_, done_dev_, forced_dev_;
   DeviceBuffer<int> meta_i32_;       // packed int32 metadata
   DeviceBuffer<int64_t> meta_i64_;   // packed int64 metadata

@@ -247,8 +247,12 @@ void TranscriptOutput::mark_all_complete() {
 void TranscriptOutput::rebuild() {
   c_lines_.clear();
   c_lines_.reserve(order.size());
+  c_words_.assign(order.size(), {});
+  size_t line_index = 0;
   for (uint64_t id : order) {
     const Line& l = lines[id];
+    std::vector<transcript_word_t>& cw = c_words_[line_index++];
+    for (const WordTiming& w : l.words) cw.push_back(transcript_word_t{w.text.c_str(), w.start, w.end, w.confidence});
     transcript_line_t c{};
     c.text = l.has_text ? l.text.c_str() : nullptr;
     c.audio_data = (l.audio && !l.audio->empty()) ? l.audio->data() : nullptr;
@@ -264,8 +268,8 @@ void TranscriptOutput::rebuild() {
     c.speaker_spans = nullptr;
     c.speaker_span_count = 0;
     c.last_transcription_latency_ms = l.latency_ms;
-    c.words = nullptr;
-    c.word_count = 0;
+    c.words = cw.empty() ? nullptr : cw.data();
+    c.word_count = cw.size();
     c_lines_.push_back(c);
   }
   transcript.lines = c_lines_.empty() ? nullptr : c_lines_.data();
@@ -412,6 +416,7 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     }
   }
   std::vector<std::vector<int32_t>> tokens;
+  std::vector<CrossAttention> xattn;  // filled when word_timestamps is on
   uint32_t latency_ms = 0;
   if (!ptrs.empty()) {
     std::lock_guard<std::mutex> lock(model_mutex_);
@@ -420,7 +425,7 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     plan.emitted = plan_emitted.data();
     plan.max_tokens = plan_max_tokens.data();
     model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens,
-                       nullptr, streaming ? &plan : nullptr);
+                       nullptr, streaming ? &plan : nullptr, options_.word_timestamps ? &xattn : nullptr);
     latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                      std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("MOONSHINE_B200_HOST_PROF"))
@@ -431,8 +436,26 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
   for (Pending& p : pend) {
     Segment& s = (*jobs[p.job].segments)[p.seg];
     if (p.run) {
+      const size_t utt = ti;
       std::vector<int32_t>& ids = tokens[ti++];
       if (p.strip_eos && !ids.empty() && ids.back() == model_->dims().eos) ids.pop_back();
+      // Word timestamps from the cross-attention the decode just produced.  Classic architectures align
+      // complete lines only (core/transcriber.cpp:1103-1117), the streaming path every decode (:1029-1070);
+      // time per frame = segment duration / memory frames, times offset by the segment start.
+      if (options_.word_timestamps && utt < xattn.size() && (streaming || s.is_complete) && ids.size() >= 2) {
+        const CrossAttention& xa = xattn[utt];
+        if (xa.steps > 0 && xa.frames > 0) {
+          const float seg_duration = (float)s.size() / (float)kSampleRate;
+          const float time_per_frame = seg_duration / (float)xa.frames;
+          std::vector<WordTiming> words =
+              align_words(xa.prob.data(), xa.heads_total, xa.steps, xa.frames, ids, time_per_frame, *tokenizer_);
+          for (WordTiming& w : words) {
+            w.start += s.start_time;
+            w.end += s.start_time;
+          }
+          p.line.words = std::move(words);
+        }
+      }
       const std::string text = tokenizer_->tokens_to_text(ids);
       if (options_.log_output_text) MSB_LOGF("Transcribed text: '%s'", text.c_str());
       p.line.text = sanitize_utf8(text);

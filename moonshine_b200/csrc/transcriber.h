@@ -13,6 +13,7 @@
 #include "../../include/moonshine_b200.h"
 #include "model.h"
 #include "tokenizer.h"
+#include "word_alignment.h"
 
 namespace msb {
 
@@ -95,6 +96,7 @@ struct Line {
   bool has_text = false;
   std::string text;
   AudioRef audio;
+  std::vector<WordTiming> words;  // absolute times (segment start added), filled when word_timestamps is on
   float start_time = 0.f, duration = 0.f;
   uint64_t id = 0;
   int8_t is_complete = 0, just_updated = 0, is_new = 0, has_text_changed = 0;
@@ -114,6 +116,7 @@ class TranscriptOutput {
 
  private:
   std::vector<transcript_line_t> c_lines_;
+  std::vector<std::vector<transcript_word_t>> c_words_;
 };
 
 struct Stream {
