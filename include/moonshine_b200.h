@@ -249,6 +249,10 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_align_words(
     char *text_out, int64_t text_cap, int32_t max_words);
 MOONSHINE_EXPORT int64_t moonshine_b200_debug_resample(const float *in, int64_t n, float in_rate,
                                                        float out_rate, float *out, int64_t cap);
+/* Microbenchmark of the decoder's operand ring (cp.async.bulk + mbarrier stages): milliseconds for `grid` CTAs
+   to each stream bytes_per_cta; shared_src != 0 makes all CTAs read the same 2 MB (L2-resident) span. */
+MOONSHINE_EXPORT float moonshine_b200_test_ring_bandwidth(int64_t bytes_per_cta, int32_t stage_bytes, int32_t stages,
+                                                          int32_t nsub, int32_t shared_src, int32_t grid);
 /* Standalone grouped-GEMM hook used by the kernel unit tests (device pointers). */
 MOONSHINE_EXPORT int32_t moonshine_b200_test_gemm(const float *dA, const float *dW, float *dC,
                                                   int32_t M, int32_t N, int32_t K, int32_t lda,

@@ -233,17 +233,35 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     tmem_ld16(lane_addr + (uint32_t)(g * 16), v0);
     if (two) tmem_ld16(lane_addr + (uint32_t)(g * 16 + 16), v1);
     tmem_ld_wait();
+    // raw maxima (scale > 0 is applied once at the end); groups entirely inside the row's valid range skip
+    // the per-column bounds checks
+    const int j0 = g * 16;
+    if (j0 >= vlo && j0 + 16 <= vhi) {
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      const int j = g * 16 + e;
-      if (j >= vlo && j < vhi) mx = fmaxf(mx, __uint_as_float(v0[e]) * p.scale);
-      if (two && j + 16 >= vlo && j + 16 < vhi) mx = fmaxf(mx, __uint_as_float(v1[e]) * p.scale);
+      for (int e = 0; e < 16; e++) mx = fmaxf(mx, __uint_as_float(v0[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; e++)
+        if (j0 + e >= vlo && j0 + e < vhi) mx = fmaxf(mx, __uint_as_float(v0[e]));
+    }
+    if (two) {
+      if (j0 + 16 >= vlo && j0 + 32 <= vhi) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) mx = fmaxf(mx, __uint_as_float(v1[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++)
+          if (j0 + 16 + e >= vlo && j0 + 16 + e < vhi) mx = fmaxf(mx, __uint_as_float(v1[e]));
+      }
     }
   }
   red_max[half][r] = mx;
   __syncthreads();
   mx = fmaxf(red_max[0][r], red_max[1][r]);
   if (mx == -INFINITY) mx = 0.f;  // rows past the utterance end: every probability is 0
+  // exp(scale * (s - max)) as one FMA + ex2: exp2(s * c - max * c), c = scale * log2(e)
+  const float c2 = p.scale * 1.4426950408889634f;
+  const float mxc = mx * c2;
 
   // ---- P V in rounds of <= 224 keys ----
   float sum = 0.f;
@@ -266,12 +284,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
         tmem_ld16(lane_addr + (uint32_t)(k0 + g * 16), v);
         tmem_ld_wait();
         float e[16];
+        const int j0 = k0 + g * 16;
+        if (j0 >= vlo && j0 + 16 <= vhi) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const int j = k0 + g * 16 + q;
-          const float ev = (j >= vlo && j < vhi) ? expf(__uint_as_float(v[q]) * p.scale - mx) : 0.f;
-          e[q] = ev;
-          sum += ev;
+          for (int q = 0; q < 16; q++) {
+            e[q] = exp2f(fmaf(__uint_as_float(v[q]), c2, -mxc));
+            sum += e[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int j = j0 + q;
+            e[q] = (j >= vlo && j < vhi) ? exp2f(fmaf(__uint_as_float(v[q]), c2, -mxc)) : 0.f;
+            sum += e[q];
+          }
         }
         const int kblock = g >> 1;                   // 32 keys per block, 16 per group
         unsigned char* base = KP + (size_t)kblock * 2 * 128 * 64;

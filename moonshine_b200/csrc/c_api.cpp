@@ -484,6 +484,16 @@ int64_t moonshine_b200_debug_resample(const float* in, int64_t n, float in_rate,
   }
 }
 
+float moonshine_b200_test_ring_bandwidth(int64_t bytes_per_cta, int32_t stage_bytes, int32_t stages, int32_t nsub,
+                                         int32_t shared_src, int32_t grid) {
+  try {
+    return ring_bandwidth_test(bytes_per_cta, stage_bytes, stages, nsub, shared_src, grid);
+  } catch (const std::exception& e) {
+    MSB_LOGF("ring bandwidth test failed: %s", e.what());
+    return -1.f;
+  }
+}
+
 int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, int32_t M, int32_t N,
                                  int32_t K, int32_t lda, int32_t ldw, int32_t ldc, const float* d_bias,
                                  int32_t act, int32_t accumulate, int32_t impl) {

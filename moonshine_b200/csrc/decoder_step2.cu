@@ -21,7 +21,9 @@ namespace msb {
 namespace {
 
 constexpr int kConsumers = 256;
-constexpr int kThreads2 = kConsumers + 32;
+constexpr int kProducers = 2;                 // producer warps: the SM overlaps at most ~2 bulk copies, and only
+                                              // when different warps issue them (scripts/ring_bw.py: 74 -> 140 GB/s)
+constexpr int kThreads2 = kConsumers + 32 * kProducers;
 constexpr int kWarpsC = kConsumers / 32;
 constexpr int kStageBytes = 32768;
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s of SM cycles: trap instead of hanging
@@ -103,27 +105,46 @@ struct Ring {
   uint64_t* empty;
   char* data;
   int ns;
-  int idx;  // chunks consumed / produced so far (thread-local, uniform)
-  __device__ __forceinline__ int stage() const { return idx % ns; }
-  __device__ __forceinline__ uint32_t parity() const { return (uint32_t)((idx / ns) & 1); }
+  // cursor over the chunk sequence (thread-local, uniform): stage index and pass parity are tracked
+  // incrementally -- `idx % ns` / `idx / ns` with a runtime ns cost two integer divisions per chunk on the
+  // critical path of every GEMV
+  int st;        // stage of the next chunk
+  uint32_t par;  // parity of the pass over the ring the next chunk belongs to
+  int turn;      // producers: chunks until this lane's next turn (0 = issue this one)
+  int who;       // producers: lane's slot among the kProducers issuing warps
+  __device__ __forceinline__ void reset(int who_) {
+    st = 0; par = 0; who = who_; turn = who_;
+  }
+  __device__ __forceinline__ int stage() const { return st; }
+  __device__ __forceinline__ uint32_t parity() const { return par; }
+  __device__ __forceinline__ void advance() {
+    if (++st == ns) { st = 0; par ^= 1u; }
+  }
+  __device__ __forceinline__ void advance_by(int n) {
+    for (int i = 0; i < n; i++) advance();
+  }
   // consumers (all 256 threads call both)
   __device__ __forceinline__ const char* acquire() {
-    mbar_wait(&full[stage()], parity());
-    return data + (size_t)stage() * kStageBytes;
+    mbar_wait(&full[st], par);
+    return data + (size_t)st * kStageBytes;
   }
   // every consumer WARP releases the stage once its lanes are done reading it
   // (empty barriers count kWarpsC arrivals): no CTA-wide sync per chunk.
   __device__ __forceinline__ void release() {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage()]);
-    idx++;
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
+    advance();
   }
-  // producer (one lane)
+  // producers (one lane per producer warp; every producer walks the whole sequence and issues its share)
   __device__ __forceinline__ void produce(const void* src, uint32_t bytes) {
-    mbar_wait(&empty[stage()], parity() ^ 1u);
-    mbar_expect_tx(&full[stage()], bytes);
-    bulk_g2s(data + (size_t)stage() * kStageBytes, src, bytes, &full[stage()]);
-    idx++;
+    if (turn == 0) {
+      mbar_wait(&empty[st], par ^ 1u);
+      mbar_expect_tx(&full[st], bytes);
+      bulk_g2s(data + (size_t)st * kStageBytes, src, bytes, &full[st]);
+      turn = kProducers;
+    }
+    turn--;
+    advance();
   }
 };
 
@@ -205,8 +226,9 @@ struct Ctx {
 
 __device__ __forceinline__ void prof_mark(Ctx& c, int tag) {
   if (c.prof != nullptr && threadIdx.x == 0 && c.prof_n < kProfSlots) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    // SM cycle counter (cheap, ~20 cycles; %globaltimer costs hundreds and perturbs sub-microsecond stages);
+    // reported as nanoseconds at the nominal 1.965 GHz -- stamps are only compared within one CTA
+    const unsigned long long t = (unsigned long long)((double)clock64() * (1.0 / 1.965));
     c.prof[(size_t)blockIdx.x * kProfSlots + c.prof_n] = (t << 8) | (unsigned)tag;
     c.prof_n++;
   }
@@ -220,7 +242,7 @@ __device__ __forceinline__ void prof_mark(Ctx& c, int tag) {
 template <int NB>
 __device__ __forceinline__ void gemm_ring_splitk(Ring& ring, const float* x, int ldx, int K, int N,
                                                  const float* __restrict__ bias, float* red,
-                                                 float* out, int ldo) {
+                                                 float* out, int ldo, Ctx* pc = nullptr) {
   const int N4 = N >> 2;
   int S = kConsumers / N4;
   if (S > K) S = K;
@@ -234,22 +256,35 @@ __device__ __forceinline__ void gemm_ring_splitk(Ring& ring, const float* x, int
   for (int k0 = 0; k0 < K; k0 += rpc) {
     const int rows = min(rpc, K - k0);
     const float4* W = reinterpret_cast<const float4*>(ring.acquire());
+    if (pc) prof_mark(*pc, 42);
     if (on) {
-#pragma unroll 4
-      for (int r = s; r < rows; r += S) {
-        const float4 w = W[r * N4 + n4];
-        const int k = k0 + r;
+      // 4 rows per trip, every shared-memory load issued before the first FMA: with two warps per
+      // scheduler the loop is latency-bound unless the loads of several rows are in flight together
+      for (int r = s; r < rows; r += 4 * S) {
+        float4 w[4];
+        float xv[4][NB];
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
-          const float xv = x[b * ldx + k];
-          acc[b][0] = fmaf(xv, w.x, acc[b][0]);
-          acc[b][1] = fmaf(xv, w.y, acc[b][1]);
-          acc[b][2] = fmaf(xv, w.z, acc[b][2]);
-          acc[b][3] = fmaf(xv, w.w, acc[b][3]);
+        for (int u = 0; u < 4; u++) {
+          const int rr = r + u * S;
+          const bool ok = rr < rows;
+          w[u] = ok ? W[rr * N4 + n4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int b = 0; b < NB; b++) xv[u][b] = ok ? x[b * ldx + k0 + rr] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            acc[b][0] = fmaf(xv[u][b], w[u].x, acc[b][0]);
+            acc[b][1] = fmaf(xv[u][b], w[u].y, acc[b][1]);
+            acc[b][2] = fmaf(xv[u][b], w[u].z, acc[b][2]);
+            acc[b][3] = fmaf(xv[u][b], w[u].w, acc[b][3]);
+          }
         }
       }
     }
     ring.release();
+    if (pc) prof_mark(*pc, 40);
   }
   if (on) {
 #pragma unroll
@@ -258,6 +293,7 @@ __device__ __forceinline__ void gemm_ring_splitk(Ring& ring, const float* x, int
           make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
   }
   csync();
+  if (pc) prof_mark(*pc, 41);
   for (int i = threadIdx.x; i < NB * N; i += kConsumers) {
     const int b = i / N, n = i - b * N;
     float v = bias ? bias[n] : 0.f;
@@ -322,7 +358,7 @@ template <int NB>
 __device__ __forceinline__ void gemm_ring(Ring& ring, const Ctx& c, const float* x, int ldx, int K, int N,
                                           const float* __restrict__ bias, float* out, int ldo) {
   if constexpr (NB <= 4) {
-    gemm_ring_splitk<NB>(ring, x, ldx, K, N, bias, c.red, out, ldo);
+    gemm_ring_splitk<NB>(ring, x, ldx, K, N, bias, c.red, out, ldo, const_cast<Ctx*>(&c));
   } else {
     // rows per thread = ceil(NB / G), G = 256 / (N/4) >= 2 for every N <= 512
     const int G = kConsumers / (N >> 2);
@@ -990,13 +1026,13 @@ __device__ void phase_logits(const DecoderParams& p, int item, Ctx& c, Ring& rin
           // arrivals -- (kWarpsC - 1) bookkeeping arrivals now, the real one from the commit
           for (int a = 0; a < kWarpsC - 1; a++) mbar_arrive(&ring.empty[ring.stage()]);
           umma_commit(&ring.empty[ring.stage()]);
-          ring.idx++;
+          ring.advance();
         }
       }
       umma_commit(c.acc_bar);
       prof_mark(c, 36);
     } else {
-      ring.idx += nchunks;
+      ring.advance_by(nchunks);
     }
     // ---- epilogue: TMEM -> registers, logits dump (optional), per-utterance argmax ----
     mbar_wait(c.acc_bar, (uint32_t)(c.acc_phase & 1));
@@ -1074,7 +1110,7 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   ring.empty = bars + 16;
   ring.data = reinterpret_cast<char*>(smem_raw + L.ring);
   ring.ns = L.ns;
-  ring.idx = 0;
+  ring.reset((threadIdx.x - kConsumers) >> 5);  // `who` is meaningful for the producer lanes only
 
   // snapshot of the done flags: the work list of this launch
   for (int b = threadIdx.x; b < p.B; b += kThreads2) active[b] = p.done[b] ? 0 : 1;
@@ -1103,8 +1139,8 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   const int n_btm = (p.B + NBM - 1) / NBM;
 
   if (threadIdx.x >= kConsumers) {
-    // ======================= producer warp =======================
-    if (threadIdx.x == kConsumers) {
+    // ======================= producer warps (one lane each) =======================
+    if ((threadIdx.x & 31) == 0) {
       for (int l = 0; l < p.L; l++) {
         for (int it = blockIdx.x; it < n_bt * p.H; it += G) produce_self(p, l, it, NB, ring, active);
         for (int it = blockIdx.x; it < n_bt * p.H; it += G) produce_cross(p, l, it, NB, ring, active);

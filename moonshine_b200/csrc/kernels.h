@@ -187,4 +187,7 @@ size_t decoder_step_smem_bytes(const DecoderParams& p);
 // previous step's candidates in its prologue).
 void launch_decoder_finalize(const DecoderParams& p, cudaStream_t stream);
 
+// Microbenchmark (ring_bench.cu): ms for every CTA of `grid` to stream bytes_per_cta through a bulk-copy ring.
+float ring_bandwidth_test(int64_t bytes_per_cta, int stage_bytes, int stages, int nsub, int shared_src, int grid);
+
 }  // namespace msb

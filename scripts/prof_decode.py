@@ -1,7 +1,7 @@
 import re,collections,sys
 names={0:'start',1:'A.resolve',2:'A.ln',3:'A.qkv',4:'A.attn',5:'A.wo',6:'A.store',7:'A.end',8:'A.bar',
 11:'B.resolve',12:'B.ln',13:'B.qc',14:'B.attn',15:'B.woc',16:'B.store',17:'B.end',18:'B.bar',
-21:'C.resolve',22:'C.ln',23:'C.fc1',25:'C.fc2',26:'C.store',27:'C.end',28:'C.bar',31:'F.end',32:'F.bar',33:'G.end',35:'G.x',36:'G.mma',37:'G.acc',38:'G.epi',34:'G.bar'}
+21:'C.resolve',22:'C.ln',23:'C.fc1',25:'C.fc2',26:'C.store',27:'C.end',28:'C.bar',31:'F.end',32:'F.bar',33:'G.end',35:'G.x',40:'g.chunk',42:'g.acq',41:'g.sync1',36:'G.mma',37:'G.acc',38:'G.epi',34:'G.bar'}
 for line in open(sys.argv[1]):
     if not line.startswith('PROF'): continue
     cta=line.split(':')[0]
