@@ -247,6 +247,16 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_align_words(
     const uint8_t *tokenizer, uint64_t tokenizer_size, const float *xattn, int32_t heads_total, int32_t steps,
     int32_t frames, const int32_t *tokens, int32_t n_tokens, float time_per_frame, float *starts, float *ends,
     char *text_out, int64_t text_cap, int32_t max_words);
+/* Text -> ids (reference: BinTokenizer::text_to_tokens, bin-tokenizer.cpp:274-404; bpe != 0 = the streaming
+   models' byte-pair mode).  Returns the id count, -1 on failure. */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_text_to_tokens(const uint8_t *tokenizer, uint64_t tokenizer_size,
+                                                             const char *text, int32_t bpe, int32_t *out,
+                                                             int32_t cap);
+/* Key-term biaser (reference: ContextBiaser, core/context-biaser.cpp): trie from the given sequences, walked
+   along `path`, bonuses added to `logits` in place. */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_biaser_apply(const int32_t *seqs, const int32_t *seq_lens,
+                                                           int32_t n_seqs, float boost, const int32_t *path,
+                                                           int32_t n_path, float *logits, int32_t vocab);
 MOONSHINE_EXPORT int64_t moonshine_b200_debug_resample(const float *in, int64_t n, float in_rate,
                                                        float out_rate, float *out, int64_t cap);
 /* Microbenchmark of the decoder's operand ring (cp.async.bulk + mbarrier stages): milliseconds for `grid` CTAs

@@ -471,6 +471,39 @@ int32_t moonshine_b200_debug_align_words(const uint8_t* tokenizer, uint64_t toke
   }
 }
 
+int32_t moonshine_b200_debug_text_to_tokens(const uint8_t* tokenizer, uint64_t tokenizer_size, const char* text,
+                                            int32_t bpe, int32_t* out, int32_t cap) {
+  try {
+    Tokenizer tk(tokenizer, (size_t)tokenizer_size);
+    const std::vector<int32_t> v = tk.text_to_tokens(std::string(text ? text : ""), bpe != 0);
+    for (int32_t i = 0; i < (int32_t)v.size() && i < cap; i++) out[i] = v[i];
+    return (int32_t)v.size();
+  } catch (const std::exception& e) {
+    return -1;
+  }
+}
+
+// Builds a biaser from `n_seqs` token sequences, walks it along `path`, then adds the bonuses to logits.
+int32_t moonshine_b200_debug_biaser_apply(const int32_t* seqs, const int32_t* seq_lens, int32_t n_seqs, float boost,
+                                          const int32_t* path, int32_t n_path, float* logits, int32_t vocab) {
+  try {
+    KeytermBiaser b;
+    b.set_boost(boost);
+    size_t o = 0;
+    for (int32_t i = 0; i < n_seqs; i++) {
+      b.add_token_sequence(std::vector<int32_t>(seqs + o, seqs + o + seq_lens[i]));
+      o += (size_t)seq_lens[i];
+    }
+    KeytermBiaser::Walk w;
+    for (int32_t i = 0; i < n_path; i++) b.advance(w, path[i]);
+    b.apply(w, logits, vocab);
+    return MOONSHINE_ERROR_NONE;
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_biaser_apply failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+}
+
 int64_t moonshine_b200_debug_resample(const float* in, int64_t n, float in_rate, float out_rate, float* out,
                                       int64_t cap) {
   try {

@@ -1,5 +1,7 @@
 #include "tokenizer.h"
 
+#include <algorithm>
+#include <cmath>
 #include <fstream>
 #include <stdexcept>
 
@@ -26,6 +28,7 @@ Tokenizer::Tokenizer(const uint8_t* data, size_t size) {
     p += len;
   }
   if (pieces_.empty()) throw std::runtime_error("No tokens found in tokenizer data");
+  build_encoder_index();
 }
 
 Tokenizer* Tokenizer::from_file(const std::string& path) {
@@ -64,6 +67,159 @@ std::string Tokenizer::tokens_to_text(const std::vector<int32_t>& tokens, bool s
   while (b < e && is_ws((unsigned char)out[b])) b++;
   while (e > b && is_ws((unsigned char)out[e - 1])) e--;
   return out.substr(b, e - b);
+}
+
+void Tokenizer::build_encoder_index() {
+  by_first_byte_.assign(256, {});
+  for (size_t i = 0; i < pieces_.size(); i++)
+    if (!pieces_[i].empty()) by_first_byte_[(uint8_t)pieces_[i][0]].push_back((int32_t)i);
+  byte_base_ = -1;
+  for (size_t start = 0; start + 256 <= pieces_.size() && byte_base_ < 0; start++) {
+    bool whole = true;
+    for (size_t o = 0; o < 256 && whole; o++)
+      whole = pieces_[start + o].size() == 1 && (uint8_t)pieces_[start + o][0] == o;
+    if (whole) byte_base_ = (int32_t)start;
+  }
+  merge_ids_.clear();
+  if (byte_base_ >= 0)
+    for (size_t i = (size_t)byte_base_ + 256; i < pieces_.size(); i++)
+      if (!pieces_[i].empty()) merge_ids_.emplace(pieces_[i], (int32_t)i);  // first (lowest) id wins
+}
+
+static std::string spaces_to_marker(const std::string& text) {
+  std::string out;
+  for (char c : text) {
+    if (c == ' ') out += "\xE2\x96\x81";
+    else out.push_back(c);
+  }
+  return out;
+}
+
+std::vector<int32_t> Tokenizer::encode_longest_match(const std::string& text) const {
+  const std::string t = spaces_to_marker(text);
+  std::vector<int32_t> out;
+  size_t pos = 0;
+  while (pos < t.size()) {
+    size_t best_len = 0;
+    int32_t best = -1;
+    for (int32_t id : by_first_byte_[(uint8_t)t[pos]]) {
+      const std::string& p = pieces_[(size_t)id];
+      if (p.size() > best_len && p.size() <= t.size() - pos && t.compare(pos, p.size(), p) == 0) {
+        best_len = p.size();
+        best = id;
+      }
+    }
+    if (best < 0) throw std::runtime_error("No match found for remaining bytes " + t.substr(pos));
+    out.push_back(best);
+    pos += best_len;
+  }
+  return out;
+}
+
+std::vector<int32_t> Tokenizer::text_to_tokens(const std::string& text, bool bpe) const {
+  if (!bpe || byte_base_ < 0) return encode_longest_match(text);
+  const std::string t = spaces_to_marker(text);
+  // one piece per UTF-8 character (a byte that cannot start a sequence stands alone)
+  std::vector<std::string> parts;
+  for (size_t o = 0; o < t.size();) {
+    const uint8_t lead = (uint8_t)t[o];
+    size_t n = (lead & 0x80) == 0 ? 1 : (lead & 0xE0) == 0xC0 ? 2 : (lead & 0xF0) == 0xE0 ? 3 : (lead & 0xF8) == 0xF0 ? 4 : 1;
+    n = std::min(n, t.size() - o);
+    parts.push_back(t.substr(o, n));
+    o += n;
+  }
+  // replay the merges: always join the adjacent pair whose spelling has the lowest id (leftmost on ties)
+  while (parts.size() > 1) {
+    int32_t best_id = -1;
+    size_t best_pos = 0;
+    for (size_t i = 0; i + 1 < parts.size(); i++) {
+      const auto it = merge_ids_.find(parts[i] + parts[i + 1]);
+      if (it != merge_ids_.end() && (best_id < 0 || it->second < best_id)) {
+        best_id = it->second;
+        best_pos = i;
+      }
+    }
+    if (best_id < 0) break;
+    parts[best_pos] += parts[best_pos + 1];
+    parts.erase(parts.begin() + (long)best_pos + 1);
+  }
+  std::vector<int32_t> out;
+  for (const std::string& part : parts) {
+    const auto it = merge_ids_.find(part);
+    if (it != merge_ids_.end()) {
+      out.push_back(it->second);
+    } else {
+      for (char c : part) out.push_back(byte_base_ + (uint8_t)c);
+    }
+  }
+  return out;
+}
+
+// ---- KeytermBiaser ----
+void KeytermBiaser::clear() {
+  nodes_.assign(1, Node{});
+  sequences_ = 0;
+}
+
+void KeytermBiaser::add_token_sequence(const std::vector<int32_t>& tokens) {
+  if (tokens.empty()) return;
+  int32_t at = 0;
+  for (int32_t tok : tokens) {
+    auto it = nodes_[(size_t)at].children.find(tok);
+    if (it != nodes_[(size_t)at].children.end()) {
+      at = it->second;
+      continue;
+    }
+    const int depth = nodes_[(size_t)at].depth + 1;
+    const int32_t child = (int32_t)nodes_.size();
+    nodes_[(size_t)at].children.emplace(tok, child);
+    nodes_.push_back(Node{});
+    nodes_.back().depth = depth;
+    at = child;
+  }
+  sequences_++;
+}
+
+std::vector<std::string> KeytermBiaser::variants_for_term(const std::string& term) {
+  const size_t b = term.find_first_not_of(" \t");
+  if (b == std::string::npos) return {};
+  const std::string t = term.substr(b, term.find_last_not_of(" \t") - b + 1);
+  if (t.compare(0, 3, "\xE2\x96\x81") == 0) return {t};  // already anchored to a word start
+  return {t, " " + t};
+}
+
+void KeytermBiaser::apply(const Walk& w, float* logits, int vocab) const {
+  if (logits == nullptr || sequences_ == 0) return;
+  std::vector<std::pair<int32_t, float>> pending;
+  for (int32_t node_index : w.active) {
+    const Node& node = nodes_[(size_t)node_index];
+    const int depth = node.depth + 1;
+    const float bonus = boost_ * (1.0f + std::log((float)depth));
+    for (const auto& child : node.children) {
+      const int32_t tok = child.first;
+      if (tok < 0 || tok >= vocab) continue;
+      bool merged = false;
+      for (auto& pb : pending) {
+        if (pb.first == tok) {
+          pb.second = std::max(pb.second, bonus);
+          merged = true;
+          break;
+        }
+      }
+      if (!merged) pending.emplace_back(tok, bonus);
+    }
+  }
+  for (const auto& pb : pending) logits[pb.first] += pb.second;
+}
+
+void KeytermBiaser::advance(Walk& w, int32_t token) const {
+  if (sequences_ == 0) return;
+  std::vector<int32_t> next{0};  // the root stays active: a term can start at any token
+  for (int32_t node_index : w.active) {
+    const auto it = nodes_[(size_t)node_index].children.find(token);
+    if (it != nodes_[(size_t)node_index].children.end()) next.push_back(it->second);
+  }
+  w.active.swap(next);
 }
 
 bool Tokenizer::starts_word(int32_t token) const {

@@ -2,6 +2,7 @@
 // BinTokenizer (core/bin-tokenizer/bin-tokenizer.cpp:46-66 record format,
 // :406-425 tokens_to_text); written from that behaviour contract.
 #pragma once
+#include <unordered_map>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -18,9 +19,46 @@ class Tokenizer {
   std::string tokens_to_text(const std::vector<int32_t>& tokens, bool skip_specials = true) const;
   // piece begins with the word-boundary marker U+2581 (core/word-alignment.cpp:158-170); false for bad ids
   bool starts_word(int32_t token) const;
+  // Text -> ids (reference: BinTokenizer::text_to_tokens, core/bin-tokenizer/bin-tokenizer.cpp:274-404).
+  // bpe = true: byte-pair encoding with the id as merge rank (what the streaming models use,
+  // core/moonshine-streaming-model.cpp:57); falls back to longest match when the vocabulary has no
+  // 256-entry byte block.  bpe = false: greedy longest match, ties to the lowest id (throws on no match).
+  std::vector<int32_t> text_to_tokens(const std::string& text, bool bpe) const;
 
  private:
+  void build_encoder_index();
+  std::vector<int32_t> encode_longest_match(const std::string& text) const;
   std::vector<std::string> pieces_;
+  std::vector<std::vector<int32_t>> by_first_byte_;        // ascending ids per first byte
+  std::unordered_map<std::string, int32_t> merge_ids_;     // piece -> lowest id, pieces after the byte block
+  int32_t byte_base_ = -1;                                 // first id of the 0x00..0xFF block, -1 if absent
+};
+
+// Key-term biasing (reference: ContextBiaser, core/context-biaser.{h,cpp}): a trie over the token spellings
+// of the key terms; before each argmax the logits of the tokens that continue an active path get
+// boost * (1 + ln(depth)), the largest bonus when several paths propose the same token.
+class KeytermBiaser {
+ public:
+  void clear();
+  void set_boost(float boost) { boost_ = boost; }
+  bool empty() const { return sequences_ == 0; }
+  void add_token_sequence(const std::vector<int32_t>& tokens);
+  static std::vector<std::string> variants_for_term(const std::string& term);
+  // Walk state is per decoded sequence: a batch keeps one Walk per utterance over the shared trie.
+  struct Walk {
+    std::vector<int32_t> active{0};
+  };
+  void apply(const Walk& w, float* logits, int vocab) const;
+  void advance(Walk& w, int32_t token) const;
+
+ private:
+  struct Node {
+    std::unordered_map<int32_t, int32_t> children;
+    int depth = 0;
+  };
+  std::vector<Node> nodes_{Node{}};
+  size_t sequences_ = 0;
+  float boost_ = 2.0f;
 };
 
 // Replace structurally invalid UTF-8 by '?' (core/transcriber.cpp:1489-1541).

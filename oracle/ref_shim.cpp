@@ -24,6 +24,13 @@ void* ref_tokenizer_new(const uint8_t* data, uint64_t size) {
     return nullptr;
   }
 }
+void* ref_tokenizer_new_bpe(const uint8_t* data, uint64_t size) {
+  try {
+    return new BinTokenizer(data, (size_t)size, "\xE2\x96\x81", BinTokenizerEncoding::kBpe);
+  } catch (...) {
+    return nullptr;
+  }
+}
 void ref_tokenizer_free(void* t) { delete static_cast<BinTokenizer*>(t); }
 
 // returns the byte length (or -1 on error); writes at most cap bytes

@@ -138,3 +138,74 @@ def test_word_alignment_matches_reference_code(ref, product):
         np.testing.assert_array_equal(sp, sr)
         np.testing.assert_array_equal(ep, er)
     ref.ref_tokenizer_free(h)
+
+
+def bpe_vocab():
+    """A small byte-fallback vocabulary: control tokens, the 256-byte block, then merged pieces."""
+    recs = [b"<unk>", b"<s>", b"</s>"] + [bytes([i]) for i in range(256)]
+    merged = ["▁", "th", "the", "▁the", "er", "in", "▁k", "ub", "▁kub", "ern", "etes", "▁kubern", "▁kubernetes",
+              "ku", "kub", "ber", "net", "es", "▁a", "an", "▁an", "é", "▁é", "lu", "min", "ous", "umin", "▁l", "日本"]
+    recs += [m.encode("utf-8") for m in merged]
+    out = bytearray()
+    for r in recs:
+        out.append(len(r))
+        out += r
+    return bytes(out), len(recs)
+
+
+def test_text_to_tokens_matches_reference_code(ref, product):
+    c = ctypes
+    ref.ref_tokenizer_new_bpe.restype = c.c_void_p
+    ref.ref_tokenizer_new_bpe.argtypes = [c.c_char_p, c.c_uint64]
+    ref.ref_text_to_tokens.restype = c.c_int32
+    ref.ref_text_to_tokens.argtypes = [c.c_void_p, c.c_char_p, c.POINTER(c.c_int32), c.c_int32]
+    blob, n = bpe_vocab()
+    texts = ["the", " the", "kubernetes", " kubernetes", "Kubernetes", "luminous", " an éclair", "日本語", "a  b",
+             "thethe", "", " ", "x", "\xff\xfe".encode("latin1").decode("latin1")]
+    for make, bpe in ((ref.ref_tokenizer_new_bpe, 1), (ref.ref_tokenizer_new, 0)):
+        h = make(blob, len(blob))
+        assert h
+        for t in texts:
+            tb = t.encode("utf-8", errors="surrogateescape") if isinstance(t, str) else t
+            a, b = np.zeros(128, np.int32), np.zeros(128, np.int32)
+            nr = ref.ref_text_to_tokens(h, tb, _i32(a), 128)
+            npd = product.moonshine_b200_debug_text_to_tokens(blob, len(blob), tb, bpe, _i32(b), 128)
+            assert nr == npd, (t, bpe, nr, npd)
+            if nr > 0:
+                np.testing.assert_array_equal(a[:nr], b[:nr])
+        ref.ref_tokenizer_free(h)
+
+
+def test_keyterm_biaser_matches_reference_code(ref, product):
+    c = ctypes
+    ref.ref_biaser_new.restype = c.c_void_p
+    for f in (ref.ref_biaser_free, ref.ref_biaser_reset):
+        f.argtypes = [c.c_void_p]
+    ref.ref_biaser_add.argtypes = [c.c_void_p, c.POINTER(c.c_int32), c.c_int32]
+    ref.ref_biaser_advance.argtypes = [c.c_void_p, c.c_int32]
+    ref.ref_biaser_apply.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.c_int32]
+    rng = np.random.default_rng(11)
+    vocab = 300
+    for trial in range(30):
+        seqs = [rng.integers(0, 40, int(rng.integers(1, 6))).astype(np.int32) for _ in range(int(rng.integers(1, 12)))]
+        if trial % 4 == 0:
+            seqs.append(np.array([5, 6, 7, vocab + 3], np.int32))   # an id outside the vocabulary is skipped
+        flat = np.concatenate(seqs).astype(np.int32)
+        lens = np.array([len(s) for s in seqs], np.int32)
+        # walk along a path that follows one sequence part of the way, with detours
+        base = seqs[int(rng.integers(0, len(seqs)))]
+        path = np.concatenate([rng.integers(0, 40, 2), base[: max(1, len(base) - 1)]]).astype(np.int32)
+        b = ref.ref_biaser_new()
+        for s in seqs:
+            ref.ref_biaser_add(b, _i32(s), len(s))
+        ref.ref_biaser_reset(b)
+        for t in path:
+            ref.ref_biaser_advance(b, int(t))
+        lr = rng.standard_normal(vocab).astype(np.float32)
+        lp = lr.copy()
+        ref.ref_biaser_apply(b, _f32(lr), vocab)
+        ref.ref_biaser_free(b)
+        rc = product.moonshine_b200_debug_biaser_apply(_i32(flat), _i32(lens), len(seqs), 2.0, _i32(path), len(path),
+                                                       _f32(lp), vocab)
+        assert rc == 0
+        np.testing.assert_array_equal(lp, lr)
