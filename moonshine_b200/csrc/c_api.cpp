@@ -42,6 +42,21 @@ int32_t int_from_string(const std::string& v) { return (int32_t)std::stol(v); }
 
 // Same key set as parse_transcriber_options (core/moonshine-c-api.cpp:129-198);
 // unknown names throw, which fails the load.
+// comma-separated key terms, trimmed, empties dropped (core/moonshine-c-api.cpp:118-127)
+std::vector<std::string> parse_keyterms(const std::string& value) {
+  std::vector<std::string> out;
+  size_t start = 0;
+  while (true) {
+    const size_t end = value.find(',', start);
+    const std::string piece = value.substr(start, end == std::string::npos ? std::string::npos : end - start);
+    const size_t b = piece.find_first_not_of(" \t");
+    if (b != std::string::npos) out.push_back(piece.substr(b, piece.find_last_not_of(" \t") - b + 1));
+    if (end == std::string::npos) break;
+    start = end + 1;
+  }
+  return out;
+}
+
 void parse_options(const moonshine_option_t* options, uint64_t count, TranscriberOptions& out) {
   for (uint64_t i = 0; i < count; i++) {
     if (options[i].name == nullptr) throw std::runtime_error("Option name is null");
@@ -62,12 +77,13 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else if (name == "log_output_text") out.log_output_text = bool_from_string(value);
     else if (name == "word_timestamps") out.word_timestamps = bool_from_string(value);
     else if (name == "identify_speakers") out.identify_speakers = bool_from_string(value);
-    else if (name == "keyterms") { if (!value.empty()) out.keyterms.push_back(value); }
+    else if (name == "keyterms") out.keyterms = parse_keyterms(value);
+    else if (name == "keyterm_boost") out.keyterm_boost = float_from_string(value);
     else if (name == "context") out.context = value;
     else if (name == "device") out.device = int_from_string(value);  // additive
     // accepted for compatibility, no effect on this runtime (ORT / CPU-side features)
     else if (name == "save_input_wav_path" || name == "log_ort_run" ||
-             name == "keyterm_boost" || name == "context_max_terms" || name == "diarization_cluster_cadence" ||
+             name == "context_max_terms" || name == "diarization_cluster_cadence" ||
              name == "diarization_analyze_cadence" || name == "diarization_cluster_window_sec" ||
              name == "diarization_model_dir" || name == "spelling_model_path" || name == "ort_providers" ||
              name == "ort_provider" || name == "coreml_cache_dir") {}
@@ -306,16 +322,21 @@ int32_t moonshine_transcribe_stream(int32_t transcriber_handle, int32_t stream_h
   STREAM_CALL(t->transcribe_stream(stream_handle, flags, out_transcript), "transcribe stream")
 }
 
-int32_t moonshine_transcriber_set_keyterms(int32_t transcriber_handle, const char*) {
+int32_t moonshine_transcriber_set_keyterms(int32_t transcriber_handle, const char* keyterms) {
   CHECK_HANDLE(t, transcriber_handle);
-  (void)t;
-  MSB_LOGF("Failed to set keyterms: only the streaming architectures decode through a path that can apply the bias");
-  return MOONSHINE_ERROR_UNKNOWN;
+  try {
+    t->set_keyterms(keyterms == nullptr ? std::vector<std::string>() : parse_keyterms(keyterms));
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to set key terms: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
 }
 int32_t moonshine_transcriber_set_context(int32_t transcriber_handle, const char*, int32_t) {
   CHECK_HANDLE(t, transcriber_handle);
   (void)t;
-  MSB_LOGF("Failed to set context: only the streaming architectures decode through a path that can apply the bias");
+  MSB_LOGF("Failed to set context: key-term extraction from a passage (ContextExtractor) is not part of moonshine-b200; "
+           "pass the terms through moonshine_transcriber_set_keyterms");
   return MOONSHINE_ERROR_UNKNOWN;
 }
 

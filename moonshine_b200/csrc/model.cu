@@ -396,7 +396,7 @@ const StreamPlan* Model::auto_plan(const uint64_t*& n_samples, int B, float max_
 
 void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B, float max_tps,
                        std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
-                       std::vector<CrossAttention>* xattn) {
+                       std::vector<CrossAttention>* xattn, LogitHook* hook) {
   CUDA_CHECK(cudaSetDevice(device_));
   tokens.clear();
   if (B <= 0) return;
@@ -440,7 +440,7 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
     }
   }
   const auto t1 = std::chrono::steady_clock::now();
-  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg, plan, xattn);
+  run(pcm_dev_.ptr, stride, n_samples, B, max_tps, tokens, dbg, plan, xattn, hook);
   if (std::getenv("MOONSHINE_B200_HOST_PROF")) {
     const auto t2 = std::chrono::steady_clock::now();
     MSB_LOGF("host profile: staging memcpy %.2f ms, h2d+run %.2f ms",
@@ -462,7 +462,7 @@ void Model::transcribe_device(const float* d_pcm, int64_t stride, const uint64_t
 
 void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
                 std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
-                std::vector<CrossAttention>* xattn) {
+                std::vector<CrossAttention>* xattn, LogitHook* hook) {
   const int D = d_.dim, I = d_.ffn, H = d_.heads, hd = d_.head_dim, V = d_.vocab;
   const int L = d_.dec_layers;
   times_ = StageTimes();
@@ -901,13 +901,71 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       p.xattn_out = xattn_dev_.ptr;
     }
   }
-  for (int t = 0; t < max_steps; t++) {
-    p.step = t;
-    p.prof = (t == prof_step) ? (void*)prof_buf.ptr : nullptr;
-    p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
-    if (use_v2) launch_decoder_step2(p, grid, stream_);
-    else launch_decoder_step(p, grid, stream_);
-    stage("decoder_step", t, 16);
+  std::vector<std::vector<int32_t>> hooked_tokens;  // filled by the host-stepped loop
+  int steps_launched = max_steps;
+  if (hook == nullptr) {
+    for (int t = 0; t < max_steps; t++) {
+      p.step = t;
+      p.prof = (t == prof_step) ? (void*)prof_buf.ptr : nullptr;
+      p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
+      if (use_v2) launch_decoder_step2(p, grid, stream_);
+      else launch_decoder_step(p, grid, stream_);
+      stage("decoder_step", t, 16);
+    }
+  } else {
+    // Host-stepped greedy loop: logits of step t come back, the hook edits them, the host's first-max argmax
+    // picks the id, and the id enters step t + 1 through the teacher-forcing input (the kernel's own EOS /
+    // budget bookkeeping then follows the host's choice).
+    const size_t fstride = (size_t)Smax + 1;
+    std::vector<int> fhost((size_t)B * fstride, 0);
+    for (int b = 0; b < B; b++) fhost[(size_t)b * fstride] = d_.bos;
+    forced_dev_.reserve(fhost.size());
+    CUDA_CHECK(cudaMemcpyAsync(forced_dev_.ptr, fhost.data(), fhost.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    logits_dbg_.reserve((size_t)B * V);
+    pin_logits_.reserve((size_t)B * V);
+    std::vector<int> col(B, 0);
+    std::vector<char> finished(B, 0);
+    hooked_tokens.assign(B, std::vector<int32_t>{(int32_t)d_.bos});
+    p.forced = forced_dev_.ptr;
+    p.logits_out = logits_dbg_.ptr;
+    int remaining = 0;
+    for (int b = 0; b < B; b++) {
+      finished[b] = mlen[b] <= 0;
+      remaining += finished[b] ? 0 : 1;
+    }
+    steps_launched = 0;
+    for (int t = 0; t < max_steps && remaining > 0; t++) {
+      p.step = t;
+      p.prof = nullptr;
+      if (use_v2) launch_decoder_step2(p, grid, stream_);
+      else launch_decoder_step(p, grid, stream_);
+      steps_launched++;
+      CUDA_CHECK(cudaMemcpyAsync(pin_logits_.ptr, logits_dbg_.ptr, (size_t)B * V * sizeof(float),
+                                 cudaMemcpyDeviceToHost, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      for (int b = 0; b < B; b++) {
+        col[b] = 0;
+        if (finished[b]) continue;
+        float* lg = pin_logits_.ptr + (size_t)b * V;
+        hook->apply(b, lg, V);
+        int best = 0;
+        float best_v = lg[0];
+        for (int v = 1; v < V; v++)
+          if (lg[v] > best_v) { best_v = lg[v]; best = v; }
+        hooked_tokens[b].push_back(best);
+        col[b] = best;
+        if (best == d_.eos || t + 1 >= mlen[b]) {
+          finished[b] = 1;
+          remaining--;
+        }
+        if (best != d_.eos) hook->advance(b, best);
+      }
+      if (t + 1 <= Smax)
+        CUDA_CHECK(cudaMemcpy2DAsync(forced_dev_.ptr + (t + 1), fstride * sizeof(int), col.data(), sizeof(int),
+                                     sizeof(int), (size_t)B, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));  // `col` is reused next step
+    }
+    p.logits_out = nullptr;
   }
   if (prof_step >= 0) {
     std::vector<unsigned long long> h((size_t)grid * 512);
@@ -924,9 +982,9 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   p.step = max_steps;
   launch_decoder_finalize(p, stream_);
   stage("decoder_finalize", -1, 32);
-  times_.decode_steps = max_steps;
-  times_.decode_launches = max_steps + 1;
-  launches += max_steps + 1;
+  times_.decode_steps = steps_launched;
+  times_.decode_launches = steps_launched + 1;
+  launches += steps_launched + 1;
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
 
   // ---------------- results ----------------
@@ -940,6 +998,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     const int n = std::min(hn[b], Smax + 1);
     tokens[b].assign(ht + (size_t)b * (Smax + 1), ht + (size_t)b * (Smax + 1) + n);
   }
+  if (hook != nullptr) tokens = hooked_tokens;  // the device list holds its own (unhooked) argmax
   if (xattn != nullptr && p.xattn_out != nullptr) {
     // [B][L][H][S][Tpad] on the device -> per utterance [L * H][steps_b][T_b]
     const size_t per_utt = (size_t)L * H * p.xattn_steps * Tpad;

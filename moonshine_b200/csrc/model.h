@@ -41,6 +41,16 @@ struct CrossAttention {
   std::vector<float> prob;
 };
 
+// Host-side logit hook (key-term biasing; reference: ContextBiaser applied between decode_step and the argmax,
+// core/transcriber.cpp:1440-1470).  When one is given, decoding is stepped from the host: every launch dumps
+// the step's logits, the hook edits them, the host takes the first-max argmax and feeds the id to the next
+// launch through the teacher-forcing input.
+struct LogitHook {
+  virtual ~LogitHook() = default;
+  virtual void apply(int utterance, float* logits, int vocab) = 0;  // before the argmax of every step
+  virtual void advance(int utterance, int token) = 0;               // after a non-EOS id was emitted
+};
+
 struct StageTimes {
   float frontend_ms = 0, encoder_ms = 0, cross_kv_ms = 0, decode_ms = 0;
   int decode_steps = 0;
@@ -61,7 +71,7 @@ class Model {
   void transcribe(const float* const* pcm, const uint64_t* n_samples, int B,
                   float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
                   DebugCapture* dbg = nullptr, const StreamPlan* plan = nullptr,
-                  std::vector<CrossAttention>* xattn = nullptr);
+                  std::vector<CrossAttention>* xattn = nullptr, LogitHook* hook = nullptr);
   // Device-resident PCM: row b at d_pcm + b * stride.
   void transcribe_device(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B,
                          float max_tokens_per_second, std::vector<std::vector<int32_t>>& tokens,
@@ -95,7 +105,7 @@ class Model {
   const StreamPlan* auto_plan(const uint64_t*& n_samples, int B, float max_tps, AutoPlan& ap) const;
   void run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, int B, float max_tps,
            std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
-           std::vector<CrossAttention>* xattn = nullptr);
+           std::vector<CrossAttention>* xattn = nullptr, LogitHook* hook = nullptr);
 
   Dims d_;
   int device_ = 0;
@@ -140,6 +150,7 @@ class Model {
   PinnedBuffer<int64_t> pin_i64_;
   PinnedBuffer<float> pin_pcm_;
   PinnedBuffer<int> pin_tokens_;
+  PinnedBuffer<float> pin_logits_;
 };
 
 }  // namespace msb

@@ -331,6 +331,7 @@ void Transcriber::load_from_directory(const std::string& path) {
   }
   tokenizer_.reset(Tokenizer::from_file(tpath));
   model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
+  if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
 }
 
 void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
@@ -343,12 +344,46 @@ void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
   }
   tokenizer_ = std::make_unique<Tokenizer>(tokenizer, tokenizer_size);
   model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
+  if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
 }
+
+void Transcriber::set_keyterms(const std::vector<std::string>& keyterms) {
+  std::lock_guard<std::mutex> lock(biaser_mutex_);
+  options_.keyterms = keyterms;
+  biaser_.clear();
+  biaser_.set_boost(options_.keyterm_boost);
+  keyterm_epoch_++;  // drops every speculative draft: the next decode of an open segment restarts as greedy
+  if (keyterms.empty()) return;
+  if (!model_) return;  // skip_transcription: nothing to tokenize against
+  if (!model_->dims().streaming) {
+    throw std::runtime_error(
+        "Key-term biasing requires one of the streaming model architectures; the loaded model does not decode "
+        "through a path that can apply it.");
+  }
+  for (const std::string& term : keyterms) {
+    for (const std::string& variant : KeytermBiaser::variants_for_term(term)) {
+      const std::vector<int32_t> ids = tokenizer_->text_to_tokens(variant, /*bpe=*/true);
+      if (!ids.empty()) biaser_.add_token_sequence(ids);
+    }
+  }
+}
+
+namespace {
+// one trie walk per utterance of the batch over the transcriber's shared trie
+struct BatchBiasHook : LogitHook {
+  const KeytermBiaser& biaser;
+  std::vector<KeytermBiaser::Walk> walks;
+  BatchBiasHook(const KeytermBiaser& b, size_t n) : biaser(b), walks(n) {}
+  void apply(int u, float* logits, int vocab) override { biaser.apply(walks[(size_t)u], logits, vocab); }
+  void advance(int u, int token) override { biaser.advance(walks[(size_t)u], token); }
+};
+}  // namespace
 
 // One batched model call for every just_updated segment of every job.
 // Reference: Transcriber::update_transcript_from_segments
 // (core/transcriber.cpp:989-1148), which runs the segments serially.
 void Transcriber::update_outputs(std::vector<Job>& jobs) {
+  std::lock_guard<std::mutex> biaser_lock(biaser_mutex_);  // held across the decode, like the reference
   struct Pending { size_t job; size_t seg; Line line; bool run; bool strip_eos; };
   std::vector<Pending> pend;
   std::vector<const float*> ptrs;
@@ -390,7 +425,7 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
           lens.push_back(s.stream_processed);
           plan_emitted.push_back(s.stream_emitted);
           int budget;
-          if (options_.use_speculative_decoding && s.stream_decoded) {
+          if (options_.use_speculative_decoding && s.stream_decoded && s.stream_keyterm_epoch == keyterm_epoch_) {
             // decode_full (moonshine-streaming-model.cpp:1217-1219): verify-then-continue returns what greedy
             // returns, but budgets by memory length and leaves EOS out
             const float dur = (float)s.stream_emitted * 0.020f;
@@ -402,6 +437,7 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
           }
           plan_max_tokens.push_back(budget);
           s.stream_decoded = true;
+          s.stream_keyterm_epoch = keyterm_epoch_;
         }
       } else if (model_) {
         if (!s.is_complete && !options_.decode_incomplete_lines) {
@@ -424,8 +460,10 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     StreamPlan plan;
     plan.emitted = plan_emitted.data();
     plan.max_tokens = plan_max_tokens.data();
+    BatchBiasHook bias_hook(biaser_, ptrs.size());
     model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens,
-                       nullptr, streaming ? &plan : nullptr, options_.word_timestamps ? &xattn : nullptr);
+                       nullptr, streaming ? &plan : nullptr, options_.word_timestamps ? &xattn : nullptr,
+                       (streaming && !biaser_.empty()) ? &bias_hook : nullptr);
     latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                      std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("MOONSHINE_B200_HOST_PROF"))

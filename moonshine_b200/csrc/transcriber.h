@@ -33,7 +33,8 @@ struct TranscriberOptions {
   bool log_output_text = false;
   bool word_timestamps = false;
   bool identify_speakers = false;
-  bool use_speculative_decoding = true;  // streaming archs: decides the token budget rule, see update_outputs
+  bool use_speculative_decoding = true;
+  float keyterm_boost = 2.0f;            // ContextBiaser::kDefaultBoost (core/context-biaser.h:44)  // streaming archs: decides the token budget rule, see update_outputs
   std::vector<std::string> keyterms;
   std::string context;
   int device = -1;  // additive option "device": CUDA ordinal (-1 = current / LOCAL_RANK)
@@ -57,6 +58,7 @@ struct Segment {
   size_t stream_processed = 0;
   int stream_emitted = 0;
   bool stream_decoded = false;
+  uint64_t stream_keyterm_epoch = 0;  // key-term list the last decode ran under
 };
 
 // The reference's VoiceActivityDetector (core/voice-activity-detector.cpp)
@@ -147,6 +149,10 @@ class Transcriber {
   void add_audio_to_stream(int32_t id, const float* audio, uint64_t n, int32_t sample_rate);
   void transcribe_stream(int32_t id, uint32_t flags, transcript_t** out);
 
+  // Key-term biasing (streaming architectures only; reference: Transcriber::set_keyterms,
+  // core/transcriber.cpp:249-296).  Throws on TINY/BASE like the reference.
+  void set_keyterms(const std::vector<std::string>& keyterms);
+
   Model* model() { return model_.get(); }
   std::mutex& model_mutex() { return model_mutex_; }
   const TranscriberOptions& options() const { return options_; }
@@ -169,6 +175,9 @@ class Transcriber {
   std::unique_ptr<Model> model_;
   std::unique_ptr<Tokenizer> tokenizer_;
   std::mutex model_mutex_;      // serialises model use (reference: stt_model_mutex)
+  std::mutex biaser_mutex_;     // reference: context_biaser_mutex, taken before the model mutex
+  KeytermBiaser biaser_;
+  uint64_t keyterm_epoch_ = 0;  // bumped by set_keyterms: earlier decodes stop counting as speculative drafts
   std::mutex batch_mutex_;      // reference: batch_stream_mutex
   std::mutex streams_mutex_;
   std::map<int32_t, std::unique_ptr<Stream>> streams_;
