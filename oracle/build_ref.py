@@ -1,7 +1,7 @@
 """Builds oracle/_ref/libmoonshine_ref_helpers.so from the reference's OWN sources, compiled where they
 lie under /root/reference (never copied): the host-side helpers of the transcription path that have no
-third-party dependency -- bin-tokenizer, resampler, word-alignment, context-biaser (+ the small utils
-they call).  The model arithmetic itself cannot be built this way: it lives in ONNX Runtime graphs that
+third-party dependency -- bin-tokenizer, resampler, word-alignment, context-biaser, voice-activity-detector
+(its Silero network replaced by a constant-probability stand-in in ref_shim.cpp) (+ the small utils they call).  The model arithmetic itself cannot be built this way: it lives in ONNX Runtime graphs that
 are not in the tree (see oracle/moonshine_oracle.py).
 
     python oracle/build_ref.py            # no-op when /root/reference is absent (the GPU box)
@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libmoonshine_ref_helpers.so")
 SOURCES = [
     "core/word-alignment.cpp", "core/bin-tokenizer/bin-tokenizer.cpp", "core/resampler.cpp",
-    "core/context-biaser.cpp", "core/moonshine-utils/string-utils.cpp", "core/moonshine-utils/debug-utils.cpp",
+    "core/context-biaser.cpp", "core/voice-activity-detector.cpp", "core/moonshine-utils/string-utils.cpp", "core/moonshine-utils/debug-utils.cpp",
     "core/moonshine-utils/file-utils.cpp",
 ]
 
@@ -30,7 +30,8 @@ def build(force: bool = False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(OUT, exist_ok=True)
-    inc = [f"-I{REF}/core", f"-I{REF}/core/bin-tokenizer", f"-I{REF}/core/moonshine-utils"]
+    inc = [f"-I{REF}/core", f"-I{REF}/core/bin-tokenizer", f"-I{REF}/core/moonshine-utils",
+           f"-I{REF}/core/third-party/onnxruntime/include"]  # headers only: silero-vad.h names ORT types
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", LIB] + inc + srcs + ["-Wl,--no-undefined"]
     subprocess.run(cmd, check=True)
     return LIB

@@ -13,9 +13,43 @@
 #include "bin-tokenizer.h"
 #include "context-biaser.h"
 #include "resampler.h"
+#include "voice-activity-detector.h"
 #include "word-alignment.h"
 
+// The reference's VoiceActivityDetector (core/voice-activity-detector.cpp) is compiled as is; its Silero
+// network (ONNX Runtime, not buildable here) is replaced by this stand-in that reports a constant speech
+// probability of 1.0 -- the same substitution moonshine-b200's Segmenter makes.
+// The ORT members of the class are left untouched (never dereferenced).
+SileroVad::SileroVad(int, int, float, int, int, int, float) {}
+SileroVad::~SileroVad() {}
+void SileroVad::predict(const std::vector<float>&, float* out_probability, int* out_flag) {
+  if (out_probability) *out_probability = 1.0f;
+  if (out_flag) *out_flag = 1;
+}
+
 extern "C" {
+
+void* ref_vad_new(float threshold, int32_t window_size, int32_t hop_size, uint64_t look_behind, uint64_t max_segment) {
+  return new VoiceActivityDetector(threshold, window_size, hop_size, (size_t)look_behind, (size_t)max_segment);
+}
+void ref_vad_free(void* v) { delete static_cast<VoiceActivityDetector*>(v); }
+void ref_vad_start(void* v) { static_cast<VoiceActivityDetector*>(v)->start(); }
+void ref_vad_stop(void* v) { static_cast<VoiceActivityDetector*>(v)->stop(); }
+void ref_vad_process(void* v, const float* audio, uint64_t n, int32_t rate) {
+  static_cast<VoiceActivityDetector*>(v)->process_audio(audio, (size_t)n, rate);
+}
+int32_t ref_vad_segment_count(void* v) { return (int32_t)static_cast<VoiceActivityDetector*>(v)->get_segments()->size(); }
+// info = {start_time, end_time, is_complete, just_updated}; returns the audio sample count
+int64_t ref_vad_segment(void* v, int32_t i, float* info, float* audio_out, int64_t cap) {
+  const VoiceActivitySegment& s = static_cast<VoiceActivityDetector*>(v)->get_segments()->at((size_t)i);
+  info[0] = s.start_time;
+  info[1] = s.end_time;
+  info[2] = s.is_complete ? 1.f : 0.f;
+  info[3] = s.just_updated ? 1.f : 0.f;
+  const int64_t m = (int64_t)s.audio_data.size() < cap ? (int64_t)s.audio_data.size() : cap;
+  if (audio_out && m > 0) std::memcpy(audio_out, s.audio_data.data(), (size_t)m * sizeof(float));
+  return (int64_t)s.audio_data.size();
+}
 
 void* ref_tokenizer_new(const uint8_t* data, uint64_t size) {
   try {
