@@ -178,7 +178,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
   L.att = take(NBmax * L.attw * 4);
   // split-K scratch only for small tiles (NB <= 4); larger tiles use the row-split mapping
   int red = (NBmax <= 4 ? 1024 * NBmax : 0) * 4;
-  if (red < (16 + 1024) * 4) red = (16 + 1024) * 4;
+  if (red < (32 + 1024) * 4) red = (32 + 1024) * 4;
   L.red = take(red);
   // the logits phase aliases [0, xg_bytes) with the bf16 hi/lo planes of its x tile
   // (nx utterances x D x 4 bytes, nx = min(64, round_up(B, 16)) but at most ~80 KB)
@@ -189,7 +189,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
     L.xg_bytes = nx * D * 4;
     if (o < L.xg_bytes) o = (L.xg_bytes + 15) / 16 * 16;
   }
-  L.ps = take(Tpad * 4);
+  L.ps = take(2 * Tpad * 4);  // one probability row per half-CTA group (phase_cross)
   L.sc = take(kWarpsC * (Smax + 4) * 4);
   L.flags = take(64 * 4);
   L.argv = take(kWarpsC * 64 * 4);
@@ -721,24 +721,42 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
   const float scale = rsqrtf((float)hd);
   const int Tpad = p.Tpad;
   const int tpr = hd >> 2;           // threads per V row (4 halves = 8 bytes each)
-  const int G = kConsumers / tpr;    // V rows per pass
-  float* ps = c.ps;
-  float* red_max = c.red;            // [8] warp maxima
-  float* red_sum = c.red + 8;        // [8] warp sums
-  float* pv = c.red + 16;            // [G][hd] PV partials (G * hd <= 1024)
+  // Thread groups.  A tile of two utterances gives each utterance its own half of the CTA (4 warps, own named
+  // barrier and scratch): the two attentions run side by side instead of back to back -- one utterance keeps only
+  // ~T/4 of 256 threads busy in the score pass anyway.  Otherwise the whole CTA walks the utterances in turn.
+  const bool halves = (NB == 2) && (Tpad <= 512);
+  const int half = halves ? (int)(threadIdx.x >> 7) : 0;
+  const int gtid = halves ? (int)(threadIdx.x & 127) : (int)threadIdx.x;
+  const int gthreads = halves ? 128 : kConsumers;
+  const int gwarps = gthreads >> 5;
+  const int gwarp = gtid >> 5;
+  auto gsync = [&]() {
+    if (halves) {
+      if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
+    } else {
+      csync();
+    }
+  };
+  const int G = gthreads / tpr;      // V rows per pass
+  float* ps = c.ps + (halves ? half * Tpad : 0);
+  float* red_max = c.red + half * 8;        // [<= 8] warp maxima
+  float* red_sum = c.red + 16 + half * 8;   // [<= 8] warp sums
+  float* pv = c.red + 32 + half * 512;      // [G][hd] PV partials (G * hd <= 1024, <= 512 per half)
   for (int b = 0; b < NB; b++) {
     if (c.flags[b]) continue;  // uniform
+    const bool mine = !halves || (b == half);  // every thread walks every chunk; only the owner group computes
     const int T = c.flags[32 + b];   // encoder length, staged by load_flags
     const float* q = c.act + b * actw;
-    // ---- scores over K^T chunks (rows = head dims); thread j owns t = 4j .. 4j+3 ----
+    // ---- scores over K^T chunks (rows = head dims); group thread j owns t = 4j .. 4j+3 ----
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const int t4 = threadIdx.x * 4;
+    const int t4 = gtid * 4;
     {
       const int rpc = rows_per_chunk_f16(hd, Tpad);
       for (int d0 = 0; d0 < hd; d0 += rpc) {
         const int nd = min(rpc, hd - d0);
         const __half* Kc = reinterpret_cast<const __half*>(ring.acquire());
-        if (t4 < Tpad) {
+        if (mine && t4 < Tpad) {
 #pragma unroll 4
           for (int d = 0; d < nd; d++) {
             const uint2 u = *reinterpret_cast<const uint2*>(Kc + d * Tpad + t4);
@@ -754,50 +772,51 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
         ring.release();
       }
     }
-    float lmax = -INFINITY;
-    if (t4 < Tpad) {
-      s0 = (t4 + 0 < T) ? s0 * scale : -INFINITY;
-      s1 = (t4 + 1 < T) ? s1 * scale : -INFINITY;
-      s2 = (t4 + 2 < T) ? s2 * scale : -INFINITY;
-      s3 = (t4 + 3 < T) ? s3 * scale : -INFINITY;
-      lmax = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    float inv = 0.f;
+    if (mine) {
+      float lmax = -INFINITY;
+      if (t4 < Tpad) {
+        s0 = (t4 + 0 < T) ? s0 * scale : -INFINITY;
+        s1 = (t4 + 1 < T) ? s1 * scale : -INFINITY;
+        s2 = (t4 + 2 < T) ? s2 * scale : -INFINITY;
+        s3 = (t4 + 3 < T) ? s3 * scale : -INFINITY;
+        lmax = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+      }
+      lmax = warp_max(lmax);
+      if (lane == 0) red_max[gwarp] = lmax;
+      gsync();                                   // (1) maxima visible; previous utterance fully done
+      float mx = red_max[0];
+      for (int i = 1; i < gwarps; i++) mx = fmaxf(mx, red_max[i]);
+      float lsum = 0.f;
+      if (t4 < Tpad) {
+        s0 = (t4 + 0 < T) ? expf(s0 - mx) : 0.f;
+        s1 = (t4 + 1 < T) ? expf(s1 - mx) : 0.f;
+        s2 = (t4 + 2 < T) ? expf(s2 - mx) : 0.f;
+        s3 = (t4 + 3 < T) ? expf(s3 - mx) : 0.f;
+        *reinterpret_cast<float4*>(&ps[t4]) = make_float4(s0, s1, s2, s3);
+        lsum = (s0 + s1) + (s2 + s3);
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0) red_sum[gwarp] = lsum;
+      gsync();                                   // (2) probabilities and sums visible
+      float tot = 0.f;
+      for (int i = 0; i < gwarps; i++) tot += red_sum[i];
+      inv = 1.0f / tot;
+      if (p.xattn_out != nullptr && t4 < Tpad) {  // word timestamps: export this (utterance, layer, head, step) row
+        float* dst = p.xattn_out +
+                     (((((int64_t)(b0 + b) * p.L + l) * H + h) * p.xattn_steps + p.step) * Tpad + t4);
+        *reinterpret_cast<float4*>(dst) = make_float4(s0 * inv, s1 * inv, s2 * inv, s3 * inv);
+      }
     }
-    lmax = warp_max(lmax);
-    if (lane == 0) red_max[warp] = lmax;
-    csync();                                   // (1) maxima visible; previous utterance fully done
-    float mx = red_max[0];
-#pragma unroll
-    for (int i = 1; i < kWarpsC; i++) mx = fmaxf(mx, red_max[i]);
-    float lsum = 0.f;
-    if (t4 < Tpad) {
-      s0 = (t4 + 0 < T) ? expf(s0 - mx) : 0.f;
-      s1 = (t4 + 1 < T) ? expf(s1 - mx) : 0.f;
-      s2 = (t4 + 2 < T) ? expf(s2 - mx) : 0.f;
-      s3 = (t4 + 3 < T) ? expf(s3 - mx) : 0.f;
-      *reinterpret_cast<float4*>(&ps[t4]) = make_float4(s0, s1, s2, s3);
-      lsum = (s0 + s1) + (s2 + s3);
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) red_sum[warp] = lsum;
-    csync();                                   // (2) probabilities and sums visible
-    float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < kWarpsC; i++) tot += red_sum[i];
-    const float inv = 1.0f / tot;
-    if (p.xattn_out != nullptr && t4 < Tpad) {  // word timestamps: export this (utterance, layer, head, step) row
-      float* dst = p.xattn_out +
-                   (((((int64_t)(b0 + b) * p.L + l) * H + h) * p.xattn_steps + p.step) * Tpad + t4);
-      *reinterpret_cast<float4*>(dst) = make_float4(s0 * inv, s1 * inv, s2 * inv, s3 * inv);
-    }
-    // ---- PV over V chunks (rows = time); thread (g, dq) owns 4 dims of rows g, g+G, ... ----
+    // ---- PV over V chunks (rows = time); group thread (g, dq) owns 4 dims of rows g, g+G, ... ----
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const int g = threadIdx.x / tpr, dq = threadIdx.x - g * tpr;
+    const int g = gtid / tpr, dq = gtid - g * tpr;
     {
       const int rpc = rows_per_chunk_f16(Tpad, hd);
       for (int r0 = 0; r0 < Tpad; r0 += rpc) {
         const int nr = min(rpc, Tpad - r0);
         const __half* Vc = reinterpret_cast<const __half*>(ring.acquire());
-        if (g < G) {
+        if (mine && g < G) {
           const int tend = min(nr, T - r0);
 #pragma unroll 4
           for (int t = g; t < tend; t += G) {
@@ -814,15 +833,17 @@ __device__ void phase_cross(const DecoderParams& p, int l, int item, Ctx& c, Rin
         ring.release();
       }
     }
-    if (g < G) *reinterpret_cast<float4*>(&pv[g * hd + dq * 4]) = make_float4(a0, a1, a2, a3);
-    csync();                                   // (3) PV partials visible
-    if (threadIdx.x < hd) {
-      float o = 0.f;
-      for (int gg = 0; gg < G; gg++) o += pv[gg * hd + threadIdx.x];
-      c.att[b * attw + threadIdx.x] = o * inv;
+    if (mine) {
+      if (g < G) *reinterpret_cast<float4*>(&pv[g * hd + dq * 4]) = make_float4(a0, a1, a2, a3);
+      gsync();                                   // (3) PV partials visible
+      if (gtid < hd) {
+        float o = 0.f;
+        for (int gg = 0; gg < G; gg++) o += pv[gg * hd + gtid];
+        c.att[b * attw + gtid] = o * inv;
+      }
     }
-    // no sync here: the next utterance only overwrites red_max before its csync (1), ps after
-    // it and pv after its csync (2) -- by then every thread has left this reduction.
+    // no sync here: the next utterance only overwrites red_max before its sync (1), ps after
+    // it and pv after its sync (2) -- by then every thread of the group has left this reduction.
   }
   csync();
   prof_mark(c, 14);
