@@ -452,7 +452,7 @@ int32_t moonshine_b200_debug_run(int32_t transcriber_handle, const float* const*
 }
 
 // ---- host-only parity hooks (no GPU needed): the product's own helpers, callable from the CPU tests that
-// compare them with the reference's compiled sources (oracle/_ref) ----
+// compare them with a build of the reference's own sources ----
 int64_t moonshine_b200_debug_tokens_to_text(const uint8_t* tokenizer, uint64_t tokenizer_size, const int32_t* ids,
                                             int32_t n, char* out, int64_t cap) {
   try {
