@@ -91,6 +91,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > kSpinLimit) __trap();
   }
 }
+// Same wait for threads that are NOT on the critical path (everyone but the MMA-issuing lane while a tensor-core
+// phase runs): back off between polls so the spinning warps do not eat the issue slots of the one thread that
+// feeds the tensor core.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+    if (clock64() - t0 > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -100,6 +120,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ---- the operand ring ----
+// ---- tcgen05 helpers (UMMA descriptors, issue, commit) ----
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;    // SBO: 8 rows * 64 B
+  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;             // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// (a, b) -> packed bf16 pairs: hi = round-to-nearest bf16, lo = bf16 of the remainder (a in the low half)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+  const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
 struct Ring {
   uint64_t* full;
   uint64_t* empty;
@@ -161,7 +213,7 @@ __device__ __forceinline__ int rows_per_chunk_f16(int rows, int cols) {
 }
 
 struct SmemLayout2 {
-  int hs, xs, act, att, red, ps, sc, flags, argv, argi, active, bars, ring, rope, bias;  // byte offsets
+  int hs, xs, act, att, red, ps, sc, flags, argv, argi, active, bars, ring, rope, bias, xp;  // byte offsets
   int actw, attw, total, ns, xg_bytes;
 };
 
@@ -198,6 +250,8 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int NBmax, int B, int D, int
   L.bias = take(2 * IC * 4);
   L.active = take(B);
   L.bars = take((2 * 16 + 2) * 8);  // ring full/empty, accumulator barrier, TMEM base
+  o = (o + 1023) / 1024 * 1024;
+  L.xp = take(((D + 31) / 32) * 2048);  // GEMV activation planes: 16 rows x (hi | lo) x 64 B per 32-wide k-block
   o = (o + 1023) / 1024 * 1024;  // SWIZZLE_64B operand chunks need 512-byte aligned stages
   L.ring = o;
   int ns = (smem_limit - o) / kStageBytes;
@@ -211,6 +265,8 @@ constexpr int kProfSlots = 512;
 struct Ctx {
   const float* rope;         // smem: cos[0..64) | sin[64..128) of this step's position
   float* bias;               // smem: staged FC1 bias chunk (2 * IC floats)
+  unsigned char* xp;         // smem: bf16 hi/lo planes of a GEMV's activation tile (16 rows, K-major SW64)
+  int mma;                   // layer GEMVs on tcgen05 (plane-packed weights)
   float* xg;                 // smem: bf16 hi/lo planes of the logits x tile (aliases hs..red)
   int nx;                    // utterances per logits pass (multiple of 16, <= 64)
   uint32_t tmem;             // TMEM base (128 columns)
@@ -354,11 +410,160 @@ __device__ __forceinline__ void gemm_ring_rows(Ring& ring, const float* x, int l
   csync();
 }
 
+// (c) tensor-core mapping (tcgen05): the weight block arrives as bf16 hi / lo A-operand planes (m-tiles of <= 128
+// output features, k-blocks of 32), the activation rows are split to B-operand planes in shared memory (N = 16
+// utterance columns, zero rows beyond NB), one thread issues the MMAs (3 split products per k16 step) into 16
+// TMEM columns per m-tile and tcgen05.commit hands each ring stage back to the producers.  Epilogue: one
+// tcgen05.ld per (warp, m-tile) gives every thread its feature's 16 utterance values.
+__device__ __forceinline__ int plane_rows(int N, int mt) { return (min(128, N - mt * 128) + 7) & ~7; }
+// k-blocks per ring chunk.  An M = 128 MMA reads 128 rows of the A plane it is pointed at even when the tile
+// has fewer (the extra output rows are ignored), so the LAST plane of a chunk must still end inside the stage:
+// (n - 1) * Rp * 128 + Rp * 64 + 128 * 64 <= kStageBytes.
+__device__ __forceinline__ int plane_kb_per_chunk(int Rp) {
+  const int n = (kStageBytes - 128 * 64 - Rp * 64) / (Rp * 128) + 1;
+  return n < 1 ? 1 : n;
+}
+
 template <int NB>
-__device__ __forceinline__ void gemm_ring(Ring& ring, const Ctx& c, const float* x, int ldx, int K, int N,
+__device__ __forceinline__ void gemm_ring_mma(Ring& ring, Ctx& c, const float* x, int ldx, int K, int N,
+                                              const float* __restrict__ bias, float* out, int ldo) {
+  static_assert(NB <= 16, "the activation tile is one N = 16 operand");
+  const int nkb = (K + 31) >> 5, n_mt = (N + 127) >> 7;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* xp = c.xp;  // [kb][hi 16 x 64 B | lo 16 x 64 B]
+  // ---- activation planes: item = (row r < 16, 16-byte chunk of 8 k) ----
+  const int chunks = nkb * 4;
+  for (int i = threadIdx.x; i < 16 * chunks; i += kConsumers) {
+    const int r = i / chunks, c8 = i - r * chunks;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = 0.f;
+    if (r < NB) {
+      const float* src = x + r * ldx + c8 * 8;
+      if (c8 * 8 < K) {
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      }
+      if (c8 * 8 + 4 < K) {
+        const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+        v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+      }
+    }
+    uint4 hi, lo;
+    split_bf16x2(v[0], v[1], hi.x, lo.x);
+    split_bf16x2(v[2], v[3], hi.y, lo.y);
+    split_bf16x2(v[4], v[5], hi.z, lo.z);
+    split_bf16x2(v[6], v[7], hi.w, lo.w);
+    const int kb = c8 >> 2, cc = c8 & 3;
+    unsigned char* base = xp + (size_t)kb * 2048 + (size_t)r * 64 + ((cc ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + 1024) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  csync();
+  // ---- MMA issue (thread 0); everyone else only moves its ring cursor ----
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (threadIdx.x == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int mt = 0; mt < n_mt; mt++) {
+      const int Rp = plane_rows(N, mt), kbc = plane_kb_per_chunk(Rp);
+      // three accumulators per m-tile, one per split product: back-to-back MMAs into ONE accumulator serialise
+      // on its latency when N is this small, independent chains overlap (summed in the epilogue)
+      const uint32_t tmem_d = c.tmem + (uint32_t)(mt * 48);
+      for (int kb0 = 0; kb0 < nkb; kb0 += kbc) {
+        const int n = min(kbc, nkb - kb0);
+        mbar_wait(&ring.full[ring.stage()], ring.parity());
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = smem_u32(ring.data + (size_t)ring.stage() * kStageBytes);
+        for (int q = 0; q < n; q++) {
+          const int kb = kb0 + q;
+          const uint32_t a_hi = a_base + (uint32_t)(q * Rp * 128), a_lo = a_hi + (uint32_t)(Rp * 64);
+          const uint32_t b_hi = smem_u32(xp + (size_t)kb * 2048), b_lo = b_hi + 1024u;
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {
+            if (kb * 32 + ks * 16 >= K) break;  // nothing but zero padding beyond K
+            const uint32_t ko = (uint32_t)ks * 32u;
+            const uint32_t acc = (kb | ks) ? 1u : 0u;
+            umma_bf16(tmem_d, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+            umma_bf16(tmem_d + 16, make_desc_sw64(a_hi + ko), make_desc_sw64(b_lo + ko), idesc, acc);
+            umma_bf16(tmem_d + 32, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+          }
+        }
+        umma_commit(&ring.empty[ring.stage()]);  // warp 0's arrival: the stage is free once the MMAs have read it
+        ring.advance();
+      }
+    }
+    umma_commit(c.acc_bar);
+  } else {
+    // The empty barriers count one arrival per consumer warp.  Warp 0's is the commit above; lane 0 of every
+    // other warp gives its own as soon as the chunk has landed (waiting for `full` keeps an arrival from
+    // slipping into the stage's previous round), which keeps 7 barrier operations off the issuing thread.
+    int total = 0;
+    for (int mt = 0; mt < n_mt; mt++) {
+      const int kbc = plane_kb_per_chunk(plane_rows(N, mt));
+      total += (nkb + kbc - 1) / kbc;
+    }
+    if (lane == 0 && warp != 0) {
+      for (int i = 0; i < total; i++) {
+        mbar_wait_relaxed(&ring.full[ring.stage()], ring.parity());
+        mbar_arrive(&ring.empty[ring.stage()]);
+        ring.advance();
+      }
+    } else {
+      ring.advance_by(total);
+    }
+  }
+  // lanes 1..31 of every warp park here (no polling) until their lane 0 is through its loop: in warp 0 that
+  // keeps the divergent waiters from taking every other issue slot of the MMA-issuing thread
+  __syncwarp();
+  // ---- epilogue: TMEM -> out[b][n] (+ bias) ----
+  mbar_wait_relaxed(c.acc_bar, (uint32_t)(c.acc_phase & 1));
+  c.acc_phase++;
+  __syncwarp();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int mt = warp >> 2; mt < n_mt; mt += 2) {  // warps 0-3 take the even m-tiles, 4-7 the odd ones
+    uint32_t r[3][16];
+#pragma unroll
+    for (int pr = 0; pr < 3; pr++) {
+      const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 48 + pr * 16);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[pr][0]), "=r"(r[pr][1]), "=r"(r[pr][2]), "=r"(r[pr][3]), "=r"(r[pr][4]), "=r"(r[pr][5]),
+            "=r"(r[pr][6]), "=r"(r[pr][7]), "=r"(r[pr][8]), "=r"(r[pr][9]), "=r"(r[pr][10]), "=r"(r[pr][11]),
+            "=r"(r[pr][12]), "=r"(r[pr][13]), "=r"(r[pr][14]), "=r"(r[pr][15])
+          : "r"(taddr)
+          : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int n = mt * 128 + (warp & 3) * 32 + lane;
+    if (n < N) {
+      const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; b++)  // small cross terms first, then the hi*hi product
+        out[b * ldo + n] = ((__uint_as_float(r[0][b]) + __uint_as_float(r[1][b])) + __uint_as_float(r[2][b])) + bv;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  csync();
+}
+
+// Which GEMVs take the tensor-core path: measured on B200, the single issuing thread plus the plane conversion
+// cost ~2 us per call, which only pays off once the SIMT mapping is compute-heavy (tiles of >= 8 utterances)
+// and the block has K >= 64 (QKV, cross-Q, FC1, FC2; not the K = head_dim output projections).  Producers and consumers apply the same rule.
+__device__ __forceinline__ bool gemv_on_tensor_cores(int mma_enabled, int NB, int K) {
+  return mma_enabled && NB >= 8 && K >= 64;
+}
+
+template <int NB>
+__device__ __forceinline__ void gemm_ring(Ring& ring, Ctx& c, const float* x, int ldx, int K, int N,
                                           const float* __restrict__ bias, float* out, int ldo) {
+  if (gemv_on_tensor_cores(c.mma, NB, K)) {
+    gemm_ring_mma<NB>(ring, c, x, ldx, K, N, bias, out, ldo);
+    return;
+  }
   if constexpr (NB <= 4) {
-    gemm_ring_splitk<NB>(ring, x, ldx, K, N, bias, c.red, out, ldo, const_cast<Ctx*>(&c));
+    gemm_ring_splitk<NB>(ring, x, ldx, K, N, bias, c.red, out, ldo, &c);
   } else {
     // rows per thread = ceil(NB / G), G = 256 / (N/4) >= 2 for every N <= 512
     const int G = kConsumers / (N >> 2);
@@ -367,6 +572,26 @@ __device__ __forceinline__ void gemm_ring(Ring& ring, const Ctx& c, const float*
     else if (NB <= 4 * G) gemm_ring_rows<NB, 4>(ring, x, ldx, K, N, bias, out, ldo);
     else gemm_ring_rows<NB, (NB + 1) / 2>(ring, x, ldx, K, N, bias, out, ldo);
   }
+}
+
+// producer side of a plane-packed [N][K] block: whole k-blocks of one m-tile per chunk
+__device__ __forceinline__ void produce_block_planes(Ring& ring, const unsigned char* P, int N, int K) {
+  const int nkb = (K + 31) >> 5, n_mt = (N + 127) >> 7;
+  size_t off = 0;
+  for (int mt = 0; mt < n_mt; mt++) {
+    const int Rp = plane_rows(N, mt), kbc = plane_kb_per_chunk(Rp);
+    for (int kb0 = 0; kb0 < nkb; kb0 += kbc) {
+      const int n = min(kbc, nkb - kb0);
+      ring.produce(P + off + (size_t)kb0 * Rp * 128, (uint32_t)(n * Rp * 128));
+    }
+    off += (size_t)Rp * nkb * 128;
+  }
+}
+__device__ __forceinline__ size_t plane_block_bytes(int N, int K) {
+  const int nkb = (K + 31) >> 5, n_mt = (N + 127) >> 7;
+  size_t rows = 0;
+  for (int mt = 0; mt < n_mt; mt++) rows += (size_t)plane_rows(N, mt);
+  return rows * nkb * 128;
 }
 
 // producer side of a [K][N] fp32 block
@@ -525,7 +750,8 @@ __device__ __forceinline__ void produce_self(const DecoderParams& p, int l, int 
   const int h = item % H, b0 = (item / H) * NB;
   if (!tile_active(p, active, NB, b0)) return;
   const DecLayerWeights& w = p.layers[l];
-  produce_block_f32(ring, w.wqkv + (int64_t)h * D * 3 * hd, D, 3 * hd);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, D)) produce_block_planes(ring, w.wqkvP + (size_t)h * plane_block_bytes(3 * hd, D), 3 * hd, D);
+  else produce_block_f32(ring, w.wqkv + (int64_t)h * D * 3 * hd, D, 3 * hd);
   if (p.step > 0) {
     for (int b = 0; b < NB; b++) {
       if (b0 + b >= p.B || !active[b0 + b]) continue;
@@ -534,7 +760,8 @@ __device__ __forceinline__ void produce_self(const DecoderParams& p, int l, int 
       produce_block_f32(ring, p.vs + bh * p.Smax * hd, p.step, hd);   // V rows [0, step)
     }
   }
-  produce_block_f32(ring, w.wo + (int64_t)h * hd * D, hd, D);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, hd)) produce_block_planes(ring, w.woP + (size_t)h * plane_block_bytes(D, hd), D, hd);
+  else produce_block_f32(ring, w.wo + (int64_t)h * hd * D, hd, D);
 }
 
 template <int NB>
@@ -689,14 +916,16 @@ __device__ __forceinline__ void produce_cross(const DecoderParams& p, int l, int
   const int h = item % H, b0 = (item / H) * NB;
   if (!tile_active(p, active, NB, b0)) return;
   const DecLayerWeights& w = p.layers[l];
-  produce_block_f32(ring, w.wqc + (int64_t)h * D * hd, D, hd);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, D)) produce_block_planes(ring, w.wqcP + (size_t)h * plane_block_bytes(hd, D), hd, D);
+  else produce_block_f32(ring, w.wqc + (int64_t)h * D * hd, D, hd);
   for (int b = 0; b < NB; b++) {
     if (b0 + b >= p.B || !active[b0 + b]) continue;
     const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
     produce_block_f16(ring, p.kc + bh * hd * p.Tpad, hd, p.Tpad);   // K^T [hd][Tpad]
     produce_block_f16(ring, p.vc + bh * p.Tpad * hd, p.Tpad, hd);   // V   [Tpad][hd]
   }
-  produce_block_f32(ring, w.woc + (int64_t)h * hd * D, hd, D);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, hd)) produce_block_planes(ring, w.wocP + (size_t)h * plane_block_bytes(D, hd), D, hd);
+  else produce_block_f32(ring, w.woc + (int64_t)h * hd * D, hd, D);
 }
 
 template <int NB>
@@ -860,8 +1089,10 @@ __device__ __forceinline__ void produce_mlp(const DecoderParams& p, int l, int i
   const int ch = item % p.n_chunk, b0 = (item / p.n_chunk) * NB;
   if (!tile_active(p, active, NB, b0)) return;
   const DecLayerWeights& w = p.layers[l];
-  produce_block_f32(ring, w.w1 + (int64_t)ch * D * 2 * IC, D, 2 * IC);
-  produce_block_f32(ring, w.w2 + (int64_t)ch * IC * D, IC, D);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, D)) produce_block_planes(ring, w.w1P + (size_t)ch * plane_block_bytes(2 * IC, D), 2 * IC, D);
+  else produce_block_f32(ring, w.w1 + (int64_t)ch * D * 2 * IC, D, 2 * IC);
+  if (gemv_on_tensor_cores(p.mma_gemv, NB, IC)) produce_block_planes(ring, w.w2P + (size_t)ch * plane_block_bytes(D, IC), D, IC);
+  else produce_block_f32(ring, w.w2 + (int64_t)ch * IC * D, IC, D);
 }
 
 template <int NB>
@@ -919,36 +1150,6 @@ __device__ void phase_final_ln(const DecoderParams& p, int item, Ctx& c, const f
 // (final-LN rows of up to 64 utterances) is split to bf16 planes in shared memory once per pass.
 // Epilogue: tcgen05.ld gives each thread one vocab row x Nx utterances; the per-utterance argmax is
 // reduced across the CTA and only (value, index) candidates leave the SM.
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
-  d |= (uint64_t)(512 >> 4) << 32;    // SBO: 8 rows * 64 B
-  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
-  d |= (uint64_t)4 << 61;             // SWIZZLE_64B
-  return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// (a, b) -> packed bf16 pairs: hi = round-to-nearest bf16, lo = bf16 of the remainder (a in the low half)
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-  const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-}
 __device__ __forceinline__ int logits_rows_per_pass(int B, int D, int xg_bytes) {
   int nx = (xg_bytes / (D * 4)) & ~15;
   if (nx > 64) nx = 64;
@@ -1043,20 +1244,26 @@ __device__ void phase_logits(const DecoderParams& p, int item, Ctx& c, Ring& rin
               umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, 1u);
             }
           }
-          // the stage is free once these MMAs have read it: the empty barrier counts kWarpsC
-          // arrivals -- (kWarpsC - 1) bookkeeping arrivals now, the real one from the commit
-          for (int a = 0; a < kWarpsC - 1; a++) mbar_arrive(&ring.empty[ring.stage()]);
-          umma_commit(&ring.empty[ring.stage()]);
+          // the stage is free once these MMAs have read it (the empty barrier counts one arrival per warp)
+          umma_commit(&ring.empty[ring.stage()]);  // warp 0's arrival; the other warps give theirs below
           ring.advance();
         }
       }
       umma_commit(c.acc_bar);
       prof_mark(c, 36);
+    } else if (lane == 0) {
+      // lane 0 of warps 1-7: this warp's arrival on every stage, given once the chunk has landed
+      for (int i = 0; i < nchunks; i++) {
+        mbar_wait_relaxed(&ring.full[ring.stage()], ring.parity());
+        mbar_arrive(&ring.empty[ring.stage()]);
+        ring.advance();
+      }
     } else {
       ring.advance_by(nchunks);
     }
+    __syncwarp();  // other lanes park here instead of polling beside the issuing thread
     // ---- epilogue: TMEM -> registers, logits dump (optional), per-utterance argmax ----
-    mbar_wait(c.acc_bar, (uint32_t)(c.acc_phase & 1));
+    mbar_wait_relaxed(c.acc_bar, (uint32_t)(c.acc_phase & 1));
     c.acc_phase++;
     __syncwarp();
     prof_mark(c, 37);
@@ -1144,9 +1351,9 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
     mbar_init(bars + 32, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 32) {  // warp 0 owns the TMEM allocation (128 columns: 2 m-tiles x <= 64 utterances)
+  if (threadIdx.x < 32) {  // warp 0 owns the TMEM allocation (256 columns: logits 2 m-tiles x <= 64 utterances; GEMVs 3 x 16 per m-tile)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                 "r"(128)
+                 "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -1200,6 +1407,8 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
     c.xg = reinterpret_cast<float*>(smem_raw);
     c.nx = logits_rows_per_pass(p.B, p.D, L.xg_bytes);
     c.tmem = tmem_base;
+    c.xp = smem_raw + L.xp;
+    c.mma = p.mma_gemv;
     c.acc_bar = bars + 32;
     c.acc_phase = 0;
   }
@@ -1273,7 +1482,7 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
   csync();
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 

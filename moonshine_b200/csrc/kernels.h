@@ -133,7 +133,23 @@ struct DecLayerWeights {
   const float* b1;     // [n_chunk][2*IC]
   const float* w2;     // [n_chunk][IC][D]
   const float* b2;     // [D]
+  // The same blocks as tensor-core operands for the v2 kernel (decoder_plane_bytes(N, K) bytes per block):
+  // bf16 hi / lo planes in UMMA K-major SWIZZLE_64B order, [m-tile of <= 128 output features][k-block of 32]
+  // [hi | lo][rows padded to 8][32 bf16] -- a ring stage receives whole k-blocks by one bulk copy.
+  const unsigned char* wqkvP;  // [H] blocks N = 3*hd, K = D
+  const unsigned char* woP;    // [H] blocks N = D,    K = hd
+  const unsigned char* wqcP;   // [H] blocks N = hd,   K = D
+  const unsigned char* wocP;   // [H] blocks N = D,    K = hd
+  const unsigned char* w1P;    // [n_chunk] blocks N = 2*IC, K = D
+  const unsigned char* w2P;    // [n_chunk] blocks N = D,    K = IC
 };
+// bytes of one plane-packed [N][K] block
+inline size_t decoder_plane_bytes(int N, int K) {
+  const int nkb = (K + 31) / 32;
+  size_t rows = 0;
+  for (int n0 = 0; n0 < N; n0 += 128) rows += (size_t)(((N - n0 < 128 ? N - n0 : 128) + 7) & ~7);
+  return rows * nkb * 128;
+}
 
 constexpr int kMaxDecLayers = 8;
 
@@ -152,6 +168,7 @@ struct DecoderParams {
   const void* embP;       // v2 logits slab: bf16 hi/lo planes in UMMA K-major SWIZZLE_64B order,
                           // [n_vchunk][m-tile][k-block of 32][plane][rows][32] (see Model::build_weights)
   int smem_limit;         // opt-in shared memory per CTA (v2 ring sizing)
+  int mma_gemv;           // v2: layer GEMVs on tcgen05 from the plane-packed blocks (else fp32 SIMT from the k-major ones)
   void* prof;             // optional [grid][512] u64 timestamps (v2 kernel, debugging)
   const float* final_ln;  // [D]
   const float* rope_cos;  // [Smax][rot/2]

@@ -28,6 +28,51 @@ struct BlobBuilder {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+uint16_t bf16_round(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bf16_value(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// Packs W[n][k] (n < N output features, k < K inputs; `get(n, k)`) as the tcgen05 A operand the v2 decoder
+// streams: per m-tile of <= 128 features and k-block of 32 inputs a bf16 hi plane and a bf16 lo plane,
+// [rows padded to 8][64 B], 16-byte chunk c of row r at position c ^ ((r >> 1) & 3) (K-major SWIZZLE_64B).
+template <typename Get>
+size_t pack_planes(BlobBuilder& bb, int N, int K, Get get) {
+  const size_t bytes = decoder_plane_bytes(N, K);
+  const size_t off = bb.add((bytes + 3) / 4);
+  uint16_t* P = reinterpret_cast<uint16_t*>(&bb.data[off]);
+  const int nkb = (K + 31) / 32;
+  size_t o = 0;  // in uint16 units
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int R = std::min(128, N - n0), Rp = (R + 7) & ~7;
+    for (int kb = 0; kb < nkb; kb++) {
+      uint16_t* hi = P + o;
+      uint16_t* lo = hi + (size_t)Rp * 32;
+      for (int r = 0; r < R; r++)
+        for (int kk = 0; kk < 32; kk++) {
+          const int k = kb * 32 + kk;
+          const float x = k < K ? get(n0 + r, k) : 0.f;
+          const uint16_t h = bf16_round(x);
+          const uint16_t l = bf16_round(x - bf16_value(h));
+          const size_t at = (size_t)r * 32 + (size_t)(((kk >> 3) ^ ((r >> 1) & 3)) * 8 + (kk & 7));
+          hi[at] = h;
+          lo[at] = l;
+        }
+      o += (size_t)Rp * 64;
+    }
+  }
+  return off;
+}
+
 }  // namespace
 
 int Model::max_len_for(uint64_t n_samples, float max_tokens_per_second) {
@@ -245,7 +290,7 @@ void Model::build_weights(const WeightFile& wf) {
   size_t o_decln = o_ones;
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
   size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
-  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2; };
+  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2, wqkvP, woP, wqcP, wocP, w1P, w2P; };
   std::vector<DecOff> dof(d_.dec_layers);
   for (int l = 0; l < d_.dec_layers; l++) {
     const std::string p = dd + "layers." + std::to_string(l) + ".";
@@ -308,6 +353,40 @@ void Model::build_weights(const WeightFile& wf) {
       for (int kk = 0; kk < IC; kk++)
         for (int n = 0; n < D; n++) w2[(size_t)kk * D + n] = f2[(size_t)n * I + c * IC + kk];
     }
+    // tensor-core copies of the same blocks (v2 kernel); LayerNorm gammas folded in exactly as above
+    if (decoder_v2_) {
+      // blocks of one kind are laid out back to back (block h at base + h * decoder_plane_bytes(N, K))
+      for (int h = 0; h < H; h++) {
+        const size_t a = pack_planes(bb, 3 * hd, D, [&](int n, int kk) {
+          const float* src = n < hd ? q : (n < 2 * hd ? k : v);
+          return src[(size_t)(h * hd + n % hd) * D + kk] * g1[kk];
+        });
+        if (h == 0) dof[l].wqkvP = a;
+      }
+      for (int h = 0; h < H; h++) {
+        const size_t a = pack_planes(bb, D, hd, [&](int n, int kk) { return o[(size_t)n * D + h * hd + kk]; });
+        if (h == 0) dof[l].woP = a;
+      }
+      for (int h = 0; h < H; h++) {
+        const size_t a = pack_planes(bb, hd, D, [&](int n, int kk) { return qc[(size_t)(h * hd + n) * D + kk] * g2[kk]; });
+        if (h == 0) dof[l].wqcP = a;
+      }
+      for (int h = 0; h < H; h++) {
+        const size_t a = pack_planes(bb, D, hd, [&](int n, int kk) { return oc[(size_t)n * D + h * hd + kk]; });
+        if (h == 0) dof[l].wocP = a;
+      }
+      for (int c = 0; c < n_chunk; c++) {
+        const size_t a = pack_planes(bb, 2 * IC, D, [&](int n, int kk) {
+          const int row = n < IC ? c * IC + n : I + c * IC + (n - IC);   // value ("up") columns, then gate
+          return f1[(size_t)row * D + kk] * g3[kk];
+        });
+        if (c == 0) dof[l].w1P = a;
+      }
+      for (int c = 0; c < n_chunk; c++) {
+        const size_t a = pack_planes(bb, D, IC, [&](int n, int kk) { return f2[(size_t)n * I + c * IC + kk]; });
+        if (c == 0) dof[l].w2P = a;
+      }
+    }
     std::memcpy(&bb.data[o_wk_all + (size_t)l * D * D], kc, sizeof(float) * D * D);
     std::memcpy(&bb.data[o_wv_all + (size_t)l * D * D], vc, sizeof(float) * D * D);
   }
@@ -339,10 +418,17 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
+  {
+    const char* e = std::getenv("MOONSHINE_B200_DECODER_GEMV");
+    dec_.mma_gemv = !(e && std::string(e) == "simt");
+  }
   for (int l = 0; l < d_.dec_layers; l++) {
     DecLayerWeights& w = dec_.layers[l];
     w.ln1 = base + dof[l].ln1; w.wqkv = base + dof[l].wqkv; w.wo = base + dof[l].wo;
     w.ln2 = base + dof[l].ln2; w.wqc = base + dof[l].wqc; w.woc = base + dof[l].woc;
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(base);
+    w.wqkvP = bytes + dof[l].wqkvP * 4; w.woP = bytes + dof[l].woP * 4; w.wqcP = bytes + dof[l].wqcP * 4;
+    w.wocP = bytes + dof[l].wocP * 4; w.w1P = bytes + dof[l].w1P * 4; w.w2P = bytes + dof[l].w2P * 4;
     w.ln3 = base + dof[l].ln3; w.w1 = base + dof[l].w1; w.b1 = base + dof[l].b1;
     w.w2 = base + dof[l].w2; w.b2 = base + dof[l].b2;
   }
