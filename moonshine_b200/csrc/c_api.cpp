@@ -80,10 +80,11 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else if (name == "keyterms") out.keyterms = parse_keyterms(value);
     else if (name == "keyterm_boost") out.keyterm_boost = float_from_string(value);
     else if (name == "context") out.context = value;
+    else if (name == "context_max_terms") out.context_max_terms = int_from_string(value);
     else if (name == "device") out.device = int_from_string(value);  // additive
     // accepted for compatibility, no effect on this runtime (ORT / CPU-side features)
     else if (name == "save_input_wav_path" || name == "log_ort_run" ||
-             name == "context_max_terms" || name == "diarization_cluster_cadence" ||
+             name == "diarization_cluster_cadence" ||
              name == "diarization_analyze_cadence" || name == "diarization_cluster_window_sec" ||
              name == "diarization_model_dir" || name == "spelling_model_path" || name == "ort_providers" ||
              name == "ort_provider" || name == "coreml_cache_dir") {}
@@ -332,12 +333,15 @@ int32_t moonshine_transcriber_set_keyterms(int32_t transcriber_handle, const cha
   }
   return MOONSHINE_ERROR_NONE;
 }
-int32_t moonshine_transcriber_set_context(int32_t transcriber_handle, const char*, int32_t) {
+int32_t moonshine_transcriber_set_context(int32_t transcriber_handle, const char* context, int32_t max_terms) {
   CHECK_HANDLE(t, transcriber_handle);
-  (void)t;
-  MSB_LOGF("Failed to set context: key-term extraction from a passage (ContextExtractor) is not part of moonshine-b200; "
-           "pass the terms through moonshine_transcriber_set_keyterms");
-  return MOONSHINE_ERROR_UNKNOWN;
+  try {
+    t->set_context(context == nullptr ? std::string() : std::string(context), max_terms);
+  } catch (const std::exception& e) {
+    MSB_LOGF("Failed to set context: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
 }
 
 const char* moonshine_transcript_to_string(const transcript_t* transcript) {
@@ -522,6 +526,26 @@ int32_t moonshine_b200_debug_biaser_apply(const int32_t* seqs, const int32_t* se
   } catch (const std::exception& e) {
     MSB_LOGF("debug_biaser_apply failed: %s", e.what());
     return MOONSHINE_ERROR_UNKNOWN;
+  }
+}
+
+// key terms of a passage, NUL-separated; returns the term count
+int32_t moonshine_b200_debug_extract_terms(const uint8_t* tokenizer, uint64_t tokenizer_size, const char* context,
+                                           int32_t max_terms, char* out, int64_t cap) {
+  try {
+    Tokenizer tk(tokenizer, (size_t)tokenizer_size);
+    const std::vector<std::string> terms = extract_key_terms(std::string(context ? context : ""), max_terms, tk);
+    int64_t o = 0;
+    for (const std::string& t2 : terms) {
+      if (o + (int64_t)t2.size() + 1 > cap) break;
+      std::memcpy(out + o, t2.data(), t2.size());
+      o += (int64_t)t2.size();
+      out[o++] = 0;
+    }
+    return (int32_t)terms.size();
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_extract_terms failed: %s", e.what());
+    return -1;
   }
 }
 

@@ -1,6 +1,7 @@
 #include "tokenizer.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <fstream>
 #include <stdexcept>
@@ -153,6 +154,109 @@ std::vector<int32_t> Tokenizer::text_to_tokens(const std::string& text, bool bpe
     }
   }
   return out;
+}
+
+// ---- key terms from a passage ----
+namespace {
+bool word_byte(unsigned char b) { return b >= 0x80 || std::isalpha(b) != 0; }
+bool digit_byte(unsigned char b) { return std::isdigit(b) != 0; }
+bool joiner_byte(unsigned char b) { return b == '\'' || b == '-'; }
+std::string strip_joiners(const std::string& w) {
+  size_t b = 0, e = w.size();
+  while (b < e && joiner_byte((unsigned char)w[b])) b++;
+  while (e > b && joiner_byte((unsigned char)w[e - 1])) e--;
+  return w.substr(b, e - b);
+}
+std::string drop_possessive(const std::string& w) {
+  const size_t n = w.size();
+  if (n >= 2 && w[n - 2] == '\'' && (w[n - 1] == 's' || w[n - 1] == 'S')) return w.substr(0, n - 2);
+  if (n >= 1 && w[n - 1] == '\'') return w.substr(0, n - 1);
+  return w;
+}
+void replace_every(std::string& s, const std::string& from, const std::string& to) {
+  size_t pos = 0;
+  while ((pos = s.find(from, pos)) != std::string::npos) {
+    s.replace(pos, from.size(), to);
+    pos += to.size();
+  }
+}
+std::vector<std::string> passage_words(const std::string& text) {
+  std::string t = text;
+  // typographic punctuation that arrives as multi-byte UTF-8 in prose
+  static const char* const kFold[][2] = {
+      {"\xe2\x80\x99", "'"}, {"\xe2\x80\x98", "'"}, {"\xe2\x80\x9c", " "}, {"\xe2\x80\x9d", " "},
+      {"\xe2\x80\x93", " "}, {"\xe2\x80\x94", " "}, {"\xe2\x80\xa6", " "}, {"\xc2\xa0", " "}};
+  for (const auto& m : kFold) replace_every(t, m[0], m[1]);
+  std::vector<std::string> words;
+  std::string cur;
+  auto flush = [&]() {
+    if (cur.empty()) return;
+    const std::string w = strip_joiners(drop_possessive(strip_joiners(cur)));
+    cur.clear();
+    size_t chars = 0;
+    bool has_digit = false;
+    for (char ch : w) {
+      if (((unsigned char)ch & 0xc0) != 0x80) chars++;
+      has_digit = has_digit || digit_byte((unsigned char)ch);
+    }
+    if (chars < 3 || has_digit) return;
+    words.push_back(w);
+  };
+  for (char ch : t) {
+    const unsigned char b = (unsigned char)ch;
+    if (word_byte(b) || digit_byte(b) || (joiner_byte(b) && !cur.empty())) cur.push_back(ch);
+    else flush();
+  }
+  flush();
+  return words;
+}
+}  // namespace
+
+std::vector<std::string> extract_key_terms(const std::string& context, int32_t max_terms, const Tokenizer& tokenizer) {
+  const size_t limit = (size_t)(max_terms > 0 ? max_terms : 200);
+  struct Form { size_t count = 0, first = 0; };
+  struct Group { std::string term; size_t term_count = 0, occurrences = 0, subwords = 0, first = 0; bool seen = false; };
+  const std::vector<std::string> words = passage_words(context);
+  std::unordered_map<std::string, Form> forms;
+  for (size_t i = 0; i < words.size(); i++) {
+    auto it = forms.emplace(words[i], Form{0, i}).first;
+    it->second.count++;
+  }
+  std::unordered_map<std::string, Group> groups;
+  for (const auto& kv : forms) {
+    std::string folded = kv.first;
+    for (char& ch : folded)
+      if ((unsigned char)ch < 0x80) ch = (char)std::tolower((unsigned char)ch);
+    Group& g = groups[folded];
+    g.occurrences += kv.second.count;
+    if (!g.seen || kv.second.count > g.term_count || (kv.second.count == g.term_count && kv.second.first < g.first)) {
+      g.term = kv.first;
+      g.term_count = kv.second.count;
+      g.first = kv.second.first;
+      g.seen = true;
+    }
+  }
+  std::vector<Group> picked;
+  for (auto& kv : groups) {
+    Group& g = kv.second;
+    try {
+      g.subwords = tokenizer.text_to_tokens(" " + g.term, /*bpe=*/true).size();
+    } catch (const std::exception&) {
+      g.subwords = 0;  // an unspellable word costs that word and nothing else
+    }
+    if (g.subwords >= 2) picked.push_back(g);
+  }
+  std::sort(picked.begin(), picked.end(), [](const Group& a, const Group& b) {
+    if (a.occurrences != b.occurrences) return a.occurrences > b.occurrences;
+    if (a.subwords != b.subwords) return a.subwords > b.subwords;
+    return a.first < b.first;
+  });
+  std::vector<std::string> terms;
+  for (const Group& g : picked) {
+    if (terms.size() >= limit) break;
+    terms.push_back(g.term);
+  }
+  return terms;
 }
 
 // ---- KeytermBiaser ----

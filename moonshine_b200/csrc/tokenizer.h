@@ -34,6 +34,12 @@ class Tokenizer {
   int32_t byte_base_ = -1;                                 // first id of the 0x00..0xFF block, -1 if absent
 };
 
+// Key terms out of a free-form passage (reference: ContextExtractor::extract, core/context-extractor.cpp:186-251):
+// words of >= 3 characters without digits, possessives stripped, case variants grouped (most frequent spelling
+// wins), kept when the tokenizer needs >= 2 subwords for " word", ranked by occurrences, then subwords, then
+// first appearance; at most max_terms (<= 0: 200).
+std::vector<std::string> extract_key_terms(const std::string& context, int32_t max_terms, const Tokenizer& tokenizer);
+
 // Key-term biasing (reference: ContextBiaser, core/context-biaser.{h,cpp}): a trie over the token spellings
 // of the key terms; before each argmax the logits of the tokens that continue an active path get
 // boost * (1 + ln(depth)), the largest bonus when several paths propose the same token.

@@ -332,6 +332,7 @@ void Transcriber::load_from_directory(const std::string& path) {
   tokenizer_.reset(Tokenizer::from_file(tpath));
   model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
   if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
+  else if (!options_.context.empty()) set_context(options_.context, options_.context_max_terms);
 }
 
 void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
@@ -345,6 +346,7 @@ void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
   tokenizer_ = std::make_unique<Tokenizer>(tokenizer, tokenizer_size);
   model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
   if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
+  else if (!options_.context.empty()) set_context(options_.context, options_.context_max_terms);
 }
 
 void Transcriber::set_keyterms(const std::vector<std::string>& keyterms) {
@@ -366,6 +368,19 @@ void Transcriber::set_keyterms(const std::vector<std::string>& keyterms) {
       if (!ids.empty()) biaser_.add_token_sequence(ids);
     }
   }
+}
+
+void Transcriber::set_context(const std::string& context, int32_t max_terms) {
+  if (!model_) {  // skip_transcription: nothing to judge words against
+    set_keyterms({});
+    return;
+  }
+  if (!model_->dims().streaming) {
+    throw std::runtime_error(
+        "Key-term biasing requires one of the streaming model architectures; the loaded model does not decode "
+        "through a path that can apply it.");
+  }
+  set_keyterms(extract_key_terms(context, max_terms, *tokenizer_));
 }
 
 namespace {

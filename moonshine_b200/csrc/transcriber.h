@@ -34,6 +34,7 @@ struct TranscriberOptions {
   bool word_timestamps = false;
   bool identify_speakers = false;
   bool use_speculative_decoding = true;
+  int32_t context_max_terms = 0;         // 0 = ContextExtractor::kDefaultMaxTerms (200)
   float keyterm_boost = 2.0f;            // ContextBiaser::kDefaultBoost (core/context-biaser.h:44)  // streaming archs: decides the token budget rule, see update_outputs
   std::vector<std::string> keyterms;
   std::string context;
@@ -152,6 +153,8 @@ class Transcriber {
   // Key-term biasing (streaming architectures only; reference: Transcriber::set_keyterms,
   // core/transcriber.cpp:249-296).  Throws on TINY/BASE like the reference.
   void set_keyterms(const std::vector<std::string>& keyterms);
+  // reference: Transcriber::set_context (core/transcriber.cpp:245-247): key terms picked out of a passage
+  void set_context(const std::string& context, int32_t max_terms);
 
   Model* model() { return model_.get(); }
   std::mutex& model_mutex() { return model_mutex_; }

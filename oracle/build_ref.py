@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libmoonshine_ref_helpers.so")
 SOURCES = [
     "core/word-alignment.cpp", "core/bin-tokenizer/bin-tokenizer.cpp", "core/resampler.cpp",
-    "core/context-biaser.cpp", "core/voice-activity-detector.cpp", "core/moonshine-utils/string-utils.cpp", "core/moonshine-utils/debug-utils.cpp",
+    "core/context-biaser.cpp", "core/context-extractor.cpp", "core/voice-activity-detector.cpp", "core/moonshine-utils/string-utils.cpp", "core/moonshine-utils/debug-utils.cpp",
     "core/moonshine-utils/file-utils.cpp",
 ]
 

@@ -12,6 +12,7 @@
 
 #include "bin-tokenizer.h"
 #include "context-biaser.h"
+#include "context-extractor.h"
 #include "resampler.h"
 #include "voice-activity-detector.h"
 #include "word-alignment.h"
@@ -116,6 +117,27 @@ int32_t ref_align_words(void* tok, const float* xattn, int32_t layers, int32_t h
     }
   }
   return (int32_t)w.size();
+}
+
+// key terms of a passage, judged by the given (BPE) tokenizer exactly as Transcriber::keyterms_from_context does
+int32_t ref_extract_terms(void* tok, const char* context, int32_t max_terms, char* out, int64_t cap) {
+  BinTokenizer* t = static_cast<BinTokenizer*>(tok);
+  const std::vector<std::string> terms =
+      ContextExtractor::extract(std::string(context), max_terms, [t](const std::string& word) -> size_t {
+        try {
+          return t->text_to_tokens<int32_t>(word).size();
+        } catch (const std::exception&) {
+          return 0;
+        }
+      });
+  int64_t o = 0;
+  for (const std::string& s : terms) {
+    if (o + (int64_t)s.size() + 1 > cap) break;
+    std::memcpy(out + o, s.data(), s.size());
+    o += (int64_t)s.size();
+    out[o++] = 0;
+  }
+  return (int32_t)terms.size();
 }
 
 void* ref_biaser_new() { return new ContextBiaser(); }

@@ -118,4 +118,28 @@ def test_keyterms_are_rejected_on_classic_architectures():
     t = api.Transcriber(model_arch=api.ModelArch.TEST, options={"vad_threshold": "0"}, memory_files=memory_files("test", 0))
     with pytest.raises(Exception):
         t.set_keyterms(["anything"])
+    with pytest.raises(Exception):
+        t.set_context("a passage with Kubernetes in it")
+    t.close()
+
+
+def test_set_context_extracts_terms_and_biases(ref):
+    """moonshine_transcriber_set_context on a streaming architecture: terms come from the passage
+    (ContextExtractor rules), the decode then runs biased; an empty passage clears the bias."""
+    arch = "test_streaming"
+    d = ARCHS[arch]
+    vocab = orc.load_tokenizer_bin(synth_tokenizer_bin(d.vocab))
+    audio = synth_audio(21, 16000 * 3)
+    t = api.Transcriber(model_arch=api.ModelArch.TEST_STREAMING, options={"vad_threshold": "0", "keyterm_boost": "60"},
+                        memory_files=memory_files(arch, 0))
+    plain = t.transcribe_without_streaming(audio).lines[0].text
+    # words spelled from vocabulary pieces (>= 3 letters, >= 2 subwords in the synthetic vocabulary)
+    marker = "▁".encode()
+    starts = [i for i in range(10, d.vocab - 3) if vocab[i].startswith(marker)]
+    word = (vocab[starts[7]] + vocab[starts[7] + 1] + vocab[starts[7] + 2]).decode().replace("▁", "")
+    t.set_context(f"The {word} meeting: {word}, again {word}.")
+    biased = t.transcribe_without_streaming(audio).lines[0].text
+    assert biased != plain and word in biased.replace(" ", "")
+    t.set_context("")
+    assert t.transcribe_without_streaming(audio).lines[0].text == plain
     t.close()

@@ -209,3 +209,38 @@ def test_keyterm_biaser_matches_reference_code(ref, product):
                                                        _f32(lp), vocab)
         assert rc == 0
         np.testing.assert_array_equal(lp, lr)
+
+
+PASSAGE = """It was the best of times at Tellson’s Bank — Tellson's, by Temple Bar, was an old-fashioned place.
+Madame Defarge knitted; madame Defarge saw nothing. The Kubernetes cluster (kubernetes v1.29, IPv6 only) restarted twice.
+Dr. Manette’s luminous notes mention luminous paint, “luminous” dials and the éclair au café …
+A well-known, so-called state-of-the-art re-entry; the Joneses' dog. an it of to. 日本語 の テキスト.
+Madame Madame Madame the the the kubernetes Kubernetes KUBERNETES --dash-- 'quoted' x-ray."""
+
+
+def test_key_term_extraction_matches_reference_code(ref, product):
+    """ContextExtractor::extract with the tokenizer-as-rarity-oracle, on a passage with typographic punctuation,
+    possessives, case variants, digits, hyphens and non-ASCII words; both the BPE and the longest-match vocabularies."""
+    c = ctypes
+    ref.ref_tokenizer_new_bpe.restype = c.c_void_p
+    ref.ref_tokenizer_new_bpe.argtypes = [c.c_char_p, c.c_uint64]
+    ref.ref_extract_terms.restype = c.c_int32
+    ref.ref_extract_terms.argtypes = [c.c_void_p, c.c_char_p, c.c_int32, c.c_char_p, c.c_int64]
+    blob, _ = bpe_vocab()
+    text = PASSAGE.encode("utf-8")
+    h = ref.ref_tokenizer_new_bpe(blob, len(blob))
+    for max_terms in (0, 3, 1, 50):
+        br, bp = ctypes.create_string_buffer(1 << 14), ctypes.create_string_buffer(1 << 14)
+        nr = ref.ref_extract_terms(h, text, max_terms, br, 1 << 14)
+        npd = product.moonshine_b200_debug_extract_terms(blob, len(blob), text, max_terms, bp, 1 << 14)
+        assert nr == npd and nr > 0
+        assert br.raw.split(b"\\0")[:nr] == bp.raw.split(b"\\0")[:npd]
+    ref.ref_tokenizer_free(h)
+    # a vocabulary without the byte block (longest match, unspellable words count as 0 subwords)
+    blob2 = synth_tokenizer_bin(400)
+    h2 = ref.ref_tokenizer_new_bpe(blob2, len(blob2))
+    br, bp = ctypes.create_string_buffer(1 << 14), ctypes.create_string_buffer(1 << 14)
+    nr = ref.ref_extract_terms(h2, b"abc abcd bcd efgh ab cdefgh", 0, br, 1 << 14)
+    npd = product.moonshine_b200_debug_extract_terms(blob2, len(blob2), b"abc abcd bcd efgh ab cdefgh", 0, bp, 1 << 14)
+    assert nr == npd and br.raw.split(b"\\0")[:max(nr, 0)] == bp.raw.split(b"\\0")[:max(npd, 0)]
+    ref.ref_tokenizer_free(h2)
