@@ -435,12 +435,10 @@ bool attention_tc_supported(int max_t, int hd, int win_past, int win_future) {
 
 void launch_attention_tc(const AttnParams& p, int groups, int max_t, cudaStream_t stream) {
   if (groups == 0 || max_t == 0) return;
-  static bool configured = false;
+  static SmemAttrCache cache;
   const size_t smem = (size_t)kQBytes + kKPBytes + kVBytes + 1024;
-  if (!configured) {
+  if (cache.needs(smem))
     CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   dim3 grid((max_t + 127) / 128, groups);
   attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
 }

@@ -124,6 +124,21 @@ inline void frontend_lengths(int64_t n, int& t1, int& t2, int& t3) {
   t3 = t2 >= 3 ? (t2 - 3) / 2 + 1 : 0;
 }
 
+// Per-device cache for cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute belongs to the (function,
+// device) pair, and one process may hold transcribers on several devices (option `device`).
+struct SmemAttrCache {
+  size_t configured[64] = {0};
+  // true when `bytes` exceeds what this device has been configured for (and records it)
+  bool needs(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (bytes <= configured[dev]) return false;
+    configured[dev] = bytes;
+    return true;
+  }
+};
+
 template <typename T>
 struct DeviceBuffer {
   T* ptr = nullptr;

@@ -731,13 +731,9 @@ __global__ void decoder_finalize_kernel(const __grid_constant__ DecoderParams p)
 template <int NB, int NBM>
 void launch_variant(const DecoderParams& p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = decoder_step_kernel<NB, NBM>;
-  static bool configured = false;
-  static size_t configured_smem = 0;
-  if (!configured || smem > configured_smem) {
+  static SmemAttrCache cache;  // one per template instantiation
+  if (cache.needs(smem == 0 ? 1 : smem))
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-    configured_smem = smem;
-  }
   void* args[] = {const_cast<DecoderParams*>(&p)};
   CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kThreads), args, smem, stream));
 }

@@ -1489,11 +1489,8 @@ decoder_step2_kernel(const __grid_constant__ DecoderParams p) {
 template <int NB, int NBM>
 void launch_variant2(const DecoderParams& p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = decoder_step2_kernel<NB, NBM>;
-  static size_t configured_smem = 0;
-  if (smem > configured_smem) {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_smem = smem;
-  }
+  static SmemAttrCache cache;  // one per template instantiation
+  if (cache.needs(smem)) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {const_cast<DecoderParams*>(&p)};
   CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kThreads2), args, smem, stream));
 }

@@ -306,12 +306,10 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
 
 void launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.groups <= 0) return;
-  static bool configured = false;
+  static SmemAttrCache cache;
   const size_t smem = (size_t)kStages * kStageBytesTC + (size_t)kRawStages * kRawBytes + 1024;
-  if (!configured) {
+  if (cache.needs(smem))
     CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, p.groups);
   static const int dbg = std::getenv("MOONSHINE_B200_GEMM_DBG") ? std::atoi(std::getenv("MOONSHINE_B200_GEMM_DBG")) : 0;
   gemm_tc_kernel<<<grid, kThreadsTC, smem, stream>>>(p, dbg);

@@ -123,23 +123,37 @@ def test_keyterms_are_rejected_on_classic_architectures():
     t.close()
 
 
-def test_set_context_extracts_terms_and_biases(ref):
+def byte_fallback_tokenizer(vocab_size):
+    """A vocabulary with the 256-entry byte block BPE needs (ids 3..258), the word-boundary marker and filler
+    pieces up to the model's vocabulary size."""
+    recs = [b"<unk>", b"<s>", b"</s>"] + [bytes([i]) for i in range(256)] + ["▁".encode()]
+    i = 0
+    while len(recs) < vocab_size:
+        recs.append(("▁" if i % 3 == 0 else "").encode() + bytes([97 + i % 26, 97 + (i // 26) % 26]))
+        i += 1
+    out = bytearray()
+    for r in recs:
+        out.append(len(r))
+        out += r
+    return bytes(out)
+
+
+def test_set_context_extracts_terms_and_biases():
     """moonshine_transcriber_set_context on a streaming architecture: terms come from the passage
     (ContextExtractor rules), the decode then runs biased; an empty passage clears the bias."""
     arch = "test_streaming"
     d = ARCHS[arch]
-    vocab = orc.load_tokenizer_bin(synth_tokenizer_bin(d.vocab))
     audio = synth_audio(21, 16000 * 3)
     t = api.Transcriber(model_arch=api.ModelArch.TEST_STREAMING, options={"vad_threshold": "0", "keyterm_boost": "60"},
-                        memory_files=memory_files(arch, 0))
+                        memory_files=memory_files(arch, 0, tokenizer=byte_fallback_tokenizer(d.vocab)))
     plain = t.transcribe_without_streaming(audio).lines[0].text
-    # words spelled from vocabulary pieces (>= 3 letters, >= 2 subwords in the synthetic vocabulary)
-    marker = "▁".encode()
-    starts = [i for i in range(10, d.vocab - 3) if vocab[i].startswith(marker)]
-    word = (vocab[starts[7]] + vocab[starts[7] + 1] + vocab[starts[7] + 2]).decode().replace("▁", "")
+    word = "Zqxj"   # no piece of the vocabulary spells it: several byte-fallback subwords
+    assert word not in plain
     t.set_context(f"The {word} meeting: {word}, again {word}.")
     biased = t.transcribe_without_streaming(audio).lines[0].text
-    assert biased != plain and word in biased.replace(" ", "")
+    # every word of the passage needs several byte-fallback subwords here, so each became a key term; with this
+    # boost the transcript is made of them
+    assert biased != plain and any(w in biased for w in (word, "meeting", "again"))
     t.set_context("")
     assert t.transcribe_without_streaming(audio).lines[0].text == plain
     t.close()
