@@ -302,8 +302,8 @@ def main():
             "roofline": {"kernel": "decoder_step2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed
-                         # ncu --set full capture of this exact workload (profiles/r1b_decoder_step2_ncu_full_tiny_b32.txt)
-                         "traffic": 194153216.0 if (model == "tiny" and B == 32) else None,
+                         # ncu --set full capture of this exact workload (profiles/r1c_decoder_step2_ncu_full_tiny_b32.txt)
+                         "traffic": 194202624.0 if (model == "tiny" and B == 32) else None,
                          "bytes_per_launch": bytes_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * N_SAMPLES * 4,
