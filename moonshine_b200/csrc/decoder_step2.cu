@@ -1,15 +1,23 @@
-// Persistent decoder-step kernel, v2: operand streaming.
+// Persistent decoder-step kernel, v2: operand streaming + tensor cores.
 //
 // Same phase structure and arithmetic order as decoder_step.cu (3 grid barriers
 // per layer, deterministic partial sums), but every operand that does not
 // depend on this step's activations -- all weights, the fp16 cross K/V cache,
 // the self K/V cache up to position step-1 -- is brought into shared memory
-// by a dedicated PRODUCER WARP through a ring of TMA bulk copies
-// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx).  The producer
-// walks the same (phase, item, operand, chunk) sequence as the 8 consumer warps
-// but never waits for the grid barriers, so the HBM/L2 stream runs ahead of the
+// by two PRODUCER WARPS through a ring of TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx).  The producers
+// walk the same (phase, item, operand, chunk) sequence as the 8 consumer warps
+// but never wait for the grid barriers, so the HBM/L2 stream runs ahead of the
 // dependency chain and the consumers only ever touch shared memory, plus the
 // small activation / partial-sum exchanges through L2.
+//
+// Tensor-core phases (tcgen05 + TMEM, bf16x3 split, fp32 accumulate):
+//   * logits: the head matrix arrives as pre-swizzled bf16 hi / lo A-operand planes; one thread issues
+//     M=128 (vocab rows) x N<=64 (utterances) MMAs, tcgen05.commit hands ring stages back, the argmax is
+//     taken in the TMEM epilogue (redux.sync + ballot);
+//   * layer GEMVs of tiles with >= 8 utterances (QKV, cross-Q, FC1, FC2): same scheme with N = 16.
+// Everything else (attention over the caches, LayerNorm, small-tile GEMVs) runs on the SIMT pipes from the ring.
+// A two-utterance tile gives each utterance its own half of the CTA in the cross-attention phase.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
