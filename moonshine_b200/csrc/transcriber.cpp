@@ -93,6 +93,14 @@ void Segmenter::process_audio(const float* audio, size_t n, int32_t sample_rate,
     audio = resampled.data();
     n = resampled.size();
   }
+  // the open segment grows by at most this call's audio (+ the look-behind when it opens): one allocation
+  // instead of a doubling chain of reallocate-and-copy steps through the hop loop
+  {
+    const size_t cap = max_segment_ ? std::min(max_segment_ + (size_t)hop_size_ + look_behind_.size(),
+                                               current_.size() + n + look_behind_.size())
+                                    : current_.size() + n + look_behind_.size();
+    if (current_.capacity() < cap) current_.reserve(cap);
+  }
   // hops are analysed where they lie; only a hop that straddles two calls is assembled
   size_t pos = 0;
   if (!remainder_.empty()) {
