@@ -135,8 +135,10 @@ void Segmenter::sync_open_segment_audio() {
 void Segmenter::process_hop(const float* hop) {
   samples_processed_ += hop_size_;
   // look-behind as a ring (the reference shifts the whole 8192-sample buffer on every hop;
-  // the content a voice start sees is identical)
-  if (!look_behind_.empty()) {
+  // the content a voice start sees is identical).  While a segment is open the ring is not needed --
+  // a start can only follow an end -- so it is left alone and rebuilt from the segment's tail at the end.
+  const bool ring_live = !previous_is_voice_ || look_behind_.size() < (size_t)hop_size_;
+  if (!look_behind_.empty() && ring_live) {
     const size_t n = look_behind_.size();
     const size_t take = std::min(n, (size_t)hop_size_);
     const float* src = hop + hop_size_ - take;
@@ -175,6 +177,15 @@ void Segmenter::process_hop(const float* hop) {
     on_voice_start();
   } else if (!is_voice && previous_is_voice_) {
     current_.insert(current_.end(), hop, hop + hop_size_);
+    if (!ring_live) {
+      // the last look_behind samples analysed = the tail of the segment that ends here (a segment begins with
+      // the look-behind of its start, so a short one still reaches back to what preceded it; zeros before that)
+      const size_t n = look_behind_.size();
+      const size_t have = std::min(n, current_.size());
+      std::fill(look_behind_.begin(), look_behind_.begin() + (n - have), 0.f);
+      std::copy(current_.end() - have, current_.end(), look_behind_.begin() + (n - have));
+      look_behind_pos_ = 0;
+    }
     on_voice_end();
     current_.clear();
     // (the reference's `look_behind.resize(count, 0.0f)` here is a no-op on an already
