@@ -370,6 +370,9 @@ int32_t moonshine_b200_transcribe_device(int32_t transcriber_handle, const float
                                          int32_t out_stride, int32_t* out_counts) {
   CHECK_HANDLE(t, transcriber_handle);
   if (t->model() == nullptr || d_pcm == nullptr || lengths == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  if (stride < 0 || count > (uint64_t)INT32_MAX) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  for (uint64_t i = 0; i < count; i++)  // a row longer than the stride would read the neighbour's (or no) memory
+    if (lengths[i] > (uint64_t)stride) return MOONSHINE_ERROR_INVALID_ARGUMENT;
   try {
     std::lock_guard<std::mutex> lock(t->model_mutex());
     std::vector<std::vector<int32_t>> tokens;

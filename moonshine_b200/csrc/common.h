@@ -86,11 +86,23 @@ inline Dims dims_from_streaming_config(uint32_t arch, const float* c, size_t n) 
   d.vocab = (int)c[9]; d.rope_den = (int)c[10]; d.rot_dim = (int)c[11]; d.rope_theta = c[12];
   d.tied = c[13] != 0.0f; d.max_seq_len = (int)c[14]; d.max_pos_emb = (int)c[15];
   d.bos = (int)c[16]; d.eos = (int)c[17]; d.n_windows = (int)c[18];
+  // every field is data from the weight file: range-check before anything divides or allocates by it
+  auto in_range = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+  if (!in_range(d.enc_dim, 4, 8192) || !in_range(d.dim, 4, 8192) || !in_range(d.enc_layers, 1, 16) ||
+      !in_range(d.dec_layers, 1, 64) || !in_range(d.heads, 1, 256) || !in_range(d.head_dim, 4, 1024) ||
+      !in_range(d.enc_ffn, 4, 65536) || !in_range(d.ffn, 4, 65536) || !in_range(d.vocab, 3, 1 << 24) ||
+      !in_range(d.rope_den, 1, d.head_dim) || !in_range(d.rot_dim, 2, d.head_dim) || (d.rot_dim & 1) ||
+      !(d.rope_theta > 0.0f) || !in_range(d.max_seq_len, 1, 1 << 20) || !in_range(d.max_pos_emb, 1, 1 << 24) ||
+      !in_range(d.bos, 0, d.vocab - 1) || !in_range(d.eos, 0, d.vocab - 1) ||
+      (int64_t)d.heads * d.head_dim != d.dim || d.enc_dim % d.heads != 0)
+    throw std::runtime_error("streaming.config: field out of range (heads * head_dim must equal the decoder size)");
   if (d.n_windows != d.enc_layers || d.n_windows > 16 || n < (size_t)19 + 2 * d.n_windows)
     throw std::runtime_error("streaming.config: one (past, future) window per encoder layer expected");
   for (int i = 0; i < d.n_windows; i++) {
     d.win_past[i] = (int)c[19 + 2 * i];
     d.win_future[i] = (int)c[20 + 2 * i];
+    if (d.win_past[i] < 0 || d.win_future[i] < 0 || d.win_past[i] > 1 << 20 || d.win_future[i] > 1 << 20)
+      throw std::runtime_error("streaming.config: negative attention window");
   }
   return d;
 }

@@ -979,6 +979,9 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   }
   if (xattn != nullptr) {
     xattn->clear();
+    if (!use_v2)
+      throw std::runtime_error("word_timestamps: the cross-attention export needs the v2 decoder kernel "
+                               "(clips up to 39 s, head_dim <= 64, hidden size a multiple of 32)");
     if (use_v2) {  // the export lives in the v2 step kernel
       p.xattn_steps = std::max(max_steps, 1);
       const size_t n = (size_t)B * L * H * p.xattn_steps * Tpad;

@@ -74,7 +74,9 @@ void Segmenter::start() {
   look_behind_.assign(look_behind_count_, 0.f);
   look_behind_pos_ = 0;
   remainder_.clear();
-  probability_window_.assign(window_size_, 0.f);
+  // The smoothing window is NOT cleared: the reference's start() calls
+  // probability_window.resize(window_size, 0.0f) on an already-sized vector, a no-op, so the averages of
+  // the previous session carry over a stop()/start() pair (core/voice-activity-detector.cpp start()).
   probability_index_ = 0;
   previous_is_voice_ = false;
 }
@@ -302,6 +304,16 @@ Transcriber::Transcriber(const TranscriberOptions& options, uint32_t model_arch)
     : options_(options), arch_(model_arch) {
   std::random_device rd;
   next_line_id_ = ((uint64_t)rd() << 32) | (uint64_t)rd();
+  if (options_.vad_threshold > 0.0f) {
+    // say it at run time, not only in the docs: there is no Silero network here
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      MSB_LOGF("vad_threshold=%g: segmentation uses a constant speech probability of 1.0 (no Silero VAD network "
+               "in this build): audio is cut by the max-segment fade only and silence is transcribed. "
+               "Set vad_threshold=0 for the reference's documented bypass.", (double)options_.vad_threshold);
+    }
+  }
 }
 
 Transcriber::~Transcriber() {}

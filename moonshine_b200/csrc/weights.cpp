@@ -1,5 +1,6 @@
 #include "weights.h"
 
+#include <cstdint>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -41,6 +42,9 @@ void parse_msw(const uint8_t* bytes, size_t size, WeightFile& out) {
     for (int d = 0; d < ndim; d++) {
       uint32_t dim = read_le<uint32_t>(bytes, size, pos);
       t.shape.push_back(dim);
+      if (dim != 0 && count > (SIZE_MAX / sizeof(float)) / dim) {
+        throw std::runtime_error("MSW: tensor '" + name + "' has an element count that overflows");
+      }
       count *= dim;
     }
     uint64_t off = read_le<uint64_t>(bytes, size, pos);

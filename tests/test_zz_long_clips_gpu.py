@@ -21,4 +21,21 @@ def test_tiny_thirteen_seconds():
 
 
 def test_streaming_fifteen_seconds():
-    check_stream_case("test_streaming", 0, "scaled", [synth_audio(74, 16000 * 15), synth_audio(75, 16000 * 11 + 7)])
+    """750 features: needs the real archs' 4096-row adapter position table (the toy streaming archs stop at 512)."""
+    check_stream_case("tiny_streaming", 0, "scaled", [synth_audio(74, 16000 * 15), synth_audio(75, 16000 * 11 + 7)])
+
+
+def test_small_streaming_multi_tile_band():
+    """500 / 470 features: more than one 128-query tile and more than 448 keys, inside the toy arch's 512-row table."""
+    check_stream_case("test_streaming", 0, "scaled", [synth_audio(76, 16000 * 10), synth_audio(77, 320 * 470 + 11)])
+
+
+def test_streaming_segment_beyond_position_table_is_a_clean_error():
+    """A segment longer than the adapter position table must fail with an error code, not crash."""
+    from tests.test_streaming_gpu import make_transcriber
+    from moonshine_b200.arch import ARCHS
+    d = ARCHS["test_streaming"]
+    t = make_transcriber("test_streaming")
+    with pytest.raises(Exception):
+        t.debug_run([synth_audio(78, 16000 * 15)], d.dim, d.vocab, max_tokens=300)
+    t.close()
