@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmoonshine.so")
 
 SOURCES = [
-    "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "ring_bench.cu", "kernels_misc.cu", "decoder_step.cu", "decoder_step2.cu", "model.cu",
+    "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "ring_bench.cu", "kernels_misc.cu", "decoder_step.cu", "decoder_step2.cu", "decoder_step3.cu", "model.cu",
     "weights.cpp", "tokenizer.cpp", "word_alignment.cpp", "transcriber.cpp", "c_api.cpp",
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -66,12 +66,18 @@ def build(force: bool = False, verbose: bool = True) -> str:
                 f.write(dig)
     if failed:
         raise RuntimeError(f"nvcc failed for {failed}")
-    if procs or force or not os.path.exists(LIB):
+    link_stamp = LIB + ".link"
+    link_cmd_id = "soname-v1"
+    if procs or force or not os.path.exists(LIB) or not os.path.exists(link_stamp) or open(link_stamp).read() != link_cmd_id:
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-lcudart", "-Xlinker", "--no-undefined"]
+                                                      "-lcudart", "-Xlinker", "--no-undefined",
+                                                      # SONAME = the name every reference binding dlopens
+                                                      "-Xlinker", "-soname=libmoonshine.so"]
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        with open(link_stamp, "w") as f:
+            f.write(link_cmd_id)
     return LIB
 
 

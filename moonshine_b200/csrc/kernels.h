@@ -142,6 +142,11 @@ struct DecLayerWeights {
   const unsigned char* wocP;   // [H] blocks N = D,    K = hd
   const unsigned char* w1P;    // [n_chunk] blocks N = 2*IC, K = D
   const unsigned char* w2P;    // [n_chunk] blocks N = D,    K = IC
+  // v3 kernel (weight-stationary GEMM jobs): whole matrices as plane-packed m-tiles of 128 output features
+  const unsigned char* wocF;   // one block N = D, K = D           (cross-attention output projection)
+  const unsigned char* w1iF;   // one block N = 2*I, K = D         rows interleaved: 2j = value j, 2j+1 = gate j
+  const float* b1i;            // [2*I] fc1 bias in the same interleaved order
+  const unsigned char* w2kF;   // [ffn_ksplit] blocks N = D, K = I / ffn_ksplit  (k-slices of fc2)
 };
 // bytes of one plane-packed [N][K] block
 inline size_t decoder_plane_bytes(int N, int K) {
@@ -193,7 +198,21 @@ struct DecoderParams {
   float* xattn_out;       // optional [B][L][H][xattn_steps][Tpad] cross-attention probabilities (word timestamps)
   int xattn_steps;
   unsigned int* barrier;  // [2] grid barrier state
+  // ---- v3 kernel ----
+  int nb_self, nb_cross;  // utterances per attention job
+  int nx;                 // utterances per GEMM job (multiple of 16, <= 64)
+  int ffn_ksplit;         // k-slices of fc2 (partial sums resolved by the next consumer)
+  int job_first[8], job_ncta[8];  // per phase kind: job j runs on CTA (first + j % ncta) % grid
+  float* attc;            // [B][D] cross-attention output (all heads), input of the output projection
+  float* act;             // [B][I] silu(gate) * value
+  unsigned int* sync3;    // [kSync3Words] epoch, error flag, one completion counter per phase (own 128-byte line)
 };
+constexpr int kSync3Words = 32 + 32 * 64;
+void launch_decoder_step3(const DecoderParams& p, int grid, cudaStream_t stream);
+size_t decoder_step3_smem_bytes(const DecoderParams& p);
+// fills nb_self / nb_cross / nx / job_first / job_ncta for batch size p.B on a grid of `grid` CTAs
+void decoder_step3_plan(DecoderParams& p, int grid);
+bool decoder_step3_supported(const DecoderParams& p);
 void launch_decoder_step(const DecoderParams& p, int grid, cudaStream_t stream);
 // v2: operands streamed through a TMA-bulk smem ring by a producer warp.
 void launch_decoder_step2(const DecoderParams& p, int grid, cudaStream_t stream);

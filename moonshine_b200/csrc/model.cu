@@ -104,6 +104,7 @@ Model::Model(const Dims& dims, const WeightFile& weights, int device) : d_(dims)
   {
     const char* e = std::getenv("MOONSHINE_B200_DECODER");
     decoder_v2_ = !(e && std::string(e) == "v1");
+    decoder_v3_ = !(e && (std::string(e) == "v1" || std::string(e) == "v2"));
   }
   build_weights(weights);
   barrier_.reserve(2);
@@ -290,7 +291,12 @@ void Model::build_weights(const WeightFile& wf) {
   size_t o_decln = o_ones;
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
   size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
-  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2, wqkvP, woP, wqcP, wocP, w1P, w2P; };
+  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2, wqkvP, woP, wqcP, wocP, w1P, w2P, wocF, w1iF, b1i, w2kF; };
+  // fc2 k-slices of the v3 kernel: the smallest split whose slice is no wider than max(D, 256) inputs
+  ffn_ksplit_ = 1;
+  for (int k = 1; k <= 16; k++)
+    if (I % k == 0 && (I / k) % 8 == 0 && I / k <= std::max(D, 256)) { ffn_ksplit_ = k; break; }
+  const int KS = ffn_ksplit_, Kc = I / KS;
   std::vector<DecOff> dof(d_.dec_layers);
   for (int l = 0; l < d_.dec_layers; l++) {
     const std::string p = dd + "layers." + std::to_string(l) + ".";
@@ -387,6 +393,21 @@ void Model::build_weights(const WeightFile& wf) {
         if (c == 0) dof[l].w2P = a;
       }
     }
+    // v3 kernel: whole matrices as 128-row m-tiles (weight-stationary GEMM jobs)
+    if (decoder_v2_) {
+      dof[l].wocF = pack_planes(bb, D, D, [&](int n, int kk) { return oc[(size_t)n * D + kk]; });
+      // fc1 rows interleaved (2j = value j, 2j+1 = gate j): the SiLU gate pairs adjacent TMEM lanes
+      dof[l].w1iF = pack_planes(bb, 2 * I, D, [&](int n, int kk) {
+        const int row = (n & 1) ? I + (n >> 1) : (n >> 1);
+        return f1[(size_t)row * D + kk] * g3[kk];
+      });
+      dof[l].b1i = bb.add((size_t)2 * I);
+      for (int n = 0; n < 2 * I; n++) bb.data[dof[l].b1i + n] = f1b[(n & 1) ? I + (n >> 1) : (n >> 1)];
+      for (int ks = 0; ks < KS; ks++) {
+        const size_t a = pack_planes(bb, D, Kc, [&](int n, int kk) { return f2[(size_t)n * I + ks * Kc + kk]; });
+        if (ks == 0) dof[l].w2kF = a;
+      }
+    }
     std::memcpy(&bb.data[o_wk_all + (size_t)l * D * D], kc, sizeof(float) * D * D);
     std::memcpy(&bb.data[o_wv_all + (size_t)l * D * D], vc, sizeof(float) * D * D);
   }
@@ -415,7 +436,7 @@ void Model::build_weights(const WeightFile& wf) {
   wv_all_ = base + o_wv_all;
   std::memset(&dec_, 0, sizeof(dec_));
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
-  dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk;
+  dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   {
@@ -429,6 +450,8 @@ void Model::build_weights(const WeightFile& wf) {
     const unsigned char* bytes = reinterpret_cast<const unsigned char*>(base);
     w.wqkvP = bytes + dof[l].wqkvP * 4; w.woP = bytes + dof[l].woP * 4; w.wqcP = bytes + dof[l].wqcP * 4;
     w.wocP = bytes + dof[l].wocP * 4; w.w1P = bytes + dof[l].w1P * 4; w.w2P = bytes + dof[l].w2P * 4;
+    w.wocF = decoder_v2_ ? bytes + dof[l].wocF * 4 : nullptr; w.w1iF = bytes + dof[l].w1iF * 4;
+    w.b1i = base + dof[l].b1i; w.w2kF = bytes + dof[l].w2kF * 4;
     w.ln3 = base + dof[l].ln3; w.w1 = base + dof[l].w1; w.b1 = base + dof[l].b1;
     w.w2 = base + dof[l].w2; w.b2 = base + dof[l].b2;
   }
@@ -917,14 +940,19 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   ks_.reserve(self_elems);
   vs_.reserve(self_elems);
   hbuf_.reserve((size_t)2 * B * D);
-  part_.reserve((size_t)(2 * H + p.n_chunk) * B * D);
+  part_.reserve((size_t)std::max(2 * H + p.n_chunk, H + p.ffn_ksplit + 1) * B * D);
+  attc_.reserve((size_t)B * D);
+  act_.reserve((size_t)B * I);
+  sync3_.reserve(kSync3Words);
+  CUDA_CHECK(cudaMemsetAsync(sync3_.ptr, 0, kSync3Words * sizeof(unsigned), stream_));
+  p.attc = attc_.ptr; p.act = act_.ptr; p.sync3 = sync3_.ptr;
   xfin_.reserve((size_t)B * D);
   cand_val_.reserve((size_t)2 * p.n_vchunk * B);
   cand_idx_.reserve((size_t)2 * p.n_vchunk * B);
   tokens_dev_.reserve((size_t)B * (Smax + 1));
   ntok_dev_.reserve(B);
   done_dev_.reserve(B);
-  pin_tokens_.reserve((size_t)B * (Smax + 1) + B + 1);
+  pin_tokens_.reserve((size_t)B * (Smax + 1) + B + 2);
   {
     int* ht = pin_tokens_.ptr;
     int* hn = ht + (size_t)B * (Smax + 1);
@@ -971,6 +999,13 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   // v2 streams operands through the smem ring; its cross-attention maps one thread to 4 key
   // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
   const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 32 == 0;
+  const bool use_v3 = use_v2 && decoder_v3_ && decoder_step3_supported(p);
+  if (use_v3) decoder_step3_plan(p, grid);
+  auto launch_step = [&]() {
+    if (use_v3) launch_decoder_step3(p, grid, stream_);
+    else if (use_v2) launch_decoder_step2(p, grid, stream_);
+    else launch_decoder_step(p, grid, stream_);
+  };
   static const int prof_step = std::getenv("MOONSHINE_B200_PROF") ? std::atoi(std::getenv("MOONSHINE_B200_PROF")) : -1;
   DeviceBuffer<unsigned long long> prof_buf;
   if (prof_step >= 0) {
@@ -997,8 +1032,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       p.step = t;
       p.prof = (t == prof_step) ? (void*)prof_buf.ptr : nullptr;
       p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
-      if (use_v2) launch_decoder_step2(p, grid, stream_);
-      else launch_decoder_step(p, grid, stream_);
+      launch_step();
       stage("decoder_step", t, 16);
     }
   } else {
@@ -1026,8 +1060,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     for (int t = 0; t < max_steps && remaining > 0; t++) {
       p.step = t;
       p.prof = nullptr;
-      if (use_v2) launch_decoder_step2(p, grid, stream_);
-      else launch_decoder_step(p, grid, stream_);
+      launch_step();
       steps_launched++;
       CUDA_CHECK(cudaMemcpyAsync(pin_logits_.ptr, logits_dbg_.ptr, (size_t)B * V * sizeof(float),
                                  cudaMemcpyDeviceToHost, stream_));
@@ -1081,7 +1114,13 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   int* hn = ht + (size_t)B * (Smax + 1);
   CUDA_CHECK(cudaMemcpyAsync(ht, tokens_dev_.ptr, (size_t)B * (Smax + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaMemcpyAsync(hn, ntok_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  unsigned* h_err = reinterpret_cast<unsigned*>(hn + B + 1);  // spare word behind the counts and the n_active staging word
+  *h_err = 0u;
+  if (use_v3) CUDA_CHECK(cudaMemcpyAsync(h_err, sync3_.ptr + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (*h_err != 0u)
+    throw std::runtime_error("decoder step watchdog: a wait inside the persistent kernel exceeded its limit "
+                             "(results discarded; the device context is intact)");
   tokens.assign(B, std::vector<int32_t>());
   for (int b = 0; b < B; b++) {
     const int n = std::min(hn[b], Smax + 1);

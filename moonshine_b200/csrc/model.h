@@ -131,6 +131,8 @@ class Model {
   int ffn_chunk_ = 64;
   int vchunk_ = 0, n_vchunk_ = 0, smem_optin_ = 0;
   bool decoder_v2_ = true;
+  bool decoder_v3_ = true;
+  int ffn_ksplit_ = 1;
 
   // rope tables (grow-only)
   DeviceBuffer<float> rope_cos_, rope_sin_;
@@ -144,7 +146,8 @@ class Model {
   DeviceBuffer<int> cand_idx_, tokens_dev_, ntok_dev_, done_dev_, forced_dev_;
   DeviceBuffer<int> meta_i32_;       // packed int32 metadata
   DeviceBuffer<int64_t> meta_i64_;   // packed int64 metadata
-  DeviceBuffer<unsigned int> barrier_;
+  DeviceBuffer<unsigned int> barrier_, sync3_;
+  DeviceBuffer<float> attc_, act_;
   DeviceBuffer<int> nactive_;
   PinnedBuffer<int> pin_i32_;
   PinnedBuffer<int64_t> pin_i64_;

@@ -23,6 +23,28 @@ SOURCES = [
 ]
 
 
+BENCH = os.path.join(OUT, "ref_benchmark")
+
+
+def build_benchmark(force: bool = False):
+    """The reference's own C++ caller of the C ABI -- core/benchmark.cpp through the header-only
+    core/moonshine-cpp.h -- compiled from the sources where they lie and linked against THIS repo's
+    libmoonshine.so (rpath relative to the binary, so it runs from the snapshot on the GPU box).  Proves
+    that a reference-side C++ client links and runs unchanged (tests/test_reference_bindings_gpu.py)."""
+    product = os.path.join(os.path.dirname(HERE), "moonshine_b200", "lib")
+    if not os.path.isdir(os.path.join(REF, "core")) or not os.path.exists(os.path.join(product, "libmoonshine.so")):
+        return BENCH if os.path.exists(BENCH) else None
+    srcs = [os.path.join(REF, "core/benchmark.cpp"), os.path.join(REF, "core/moonshine-utils/file-utils.cpp")]
+    deps = srcs + [os.path.join(REF, "core/moonshine-cpp.h"), os.path.join(REF, "core/moonshine-c-api.h")]
+    if not force and os.path.exists(BENCH) and all(os.path.getmtime(BENCH) >= os.path.getmtime(s) for s in deps):
+        return BENCH
+    os.makedirs(OUT, exist_ok=True)
+    cmd = ["g++", "-std=c++20", "-O2", "-o", BENCH, f"-I{REF}/core", f"-I{REF}/core/moonshine-utils"] + srcs + [
+        f"-L{product}", "-lmoonshine", "-Wl,-rpath,$ORIGIN/../../moonshine_b200/lib", "-Wl,--no-undefined", "-pthread"]
+    subprocess.run(cmd, check=True)
+    return BENCH
+
+
 def build(force: bool = False):
     if not os.path.isdir(os.path.join(REF, "core")):
         return LIB if os.path.exists(LIB) else None
@@ -39,3 +61,4 @@ def build(force: bool = False):
 
 if __name__ == "__main__":
     print(build("--force" in sys.argv))
+    print(build_benchmark("--force" in sys.argv))
