@@ -257,6 +257,10 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_text_to_tokens(const uint8_t *toke
 MOONSHINE_EXPORT int32_t moonshine_b200_debug_biaser_apply(const int32_t *seqs, const int32_t *seq_lens,
                                                            int32_t n_seqs, float boost, const int32_t *path,
                                                            int32_t n_path, float *logits, int32_t vocab);
+/* The same bonuses through the sparse form the on-device path uploads (dense root bonuses + per-step pairs). */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_biaser_apply_sparse(const int32_t *seqs, const int32_t *seq_lens,
+                                                                  int32_t n_seqs, float boost, const int32_t *path,
+                                                                  int32_t n_path, float *logits, int32_t vocab);
 /* Key terms of a passage (reference: ContextExtractor::extract, core/context-extractor.cpp), NUL-separated. */
 MOONSHINE_EXPORT int32_t moonshine_b200_debug_extract_terms(const uint8_t *tokenizer, uint64_t tokenizer_size,
                                                             const char *context, int32_t max_terms, char *out,

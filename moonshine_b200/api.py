@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "moonshine_b200_get_stream", "moonshine_b200_set_timing", "moonshine_b200_last_timings",
     "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial",
     "moonshine_b200_debug_tokens_to_text", "moonshine_b200_debug_resample", "moonshine_b200_debug_align_words", "moonshine_b200_test_ring_bandwidth",
-    "moonshine_b200_debug_text_to_tokens", "moonshine_b200_debug_biaser_apply", "moonshine_b200_debug_extract_terms", "moonshine_b200_test_gemm",
+    "moonshine_b200_debug_text_to_tokens", "moonshine_b200_debug_biaser_apply", "moonshine_b200_debug_biaser_apply_sparse", "moonshine_b200_debug_extract_terms", "moonshine_b200_test_gemm",
 ]
 
 _lib = None
@@ -190,6 +190,8 @@ def load_library() -> ctypes.CDLL:
     lib.moonshine_b200_debug_biaser_apply.restype = c.c_int32
     lib.moonshine_b200_debug_biaser_apply.argtypes = [c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.c_int32, c.c_float,
                                                       c.POINTER(c.c_int32), c.c_int32, c.POINTER(c.c_float), c.c_int32]
+    lib.moonshine_b200_debug_biaser_apply_sparse.restype = c.c_int32
+    lib.moonshine_b200_debug_biaser_apply_sparse.argtypes = lib.moonshine_b200_debug_biaser_apply.argtypes
     lib.moonshine_b200_debug_extract_terms.restype = c.c_int32
     lib.moonshine_b200_debug_extract_terms.argtypes = [c.c_void_p, c.c_uint64, c.c_char_p, c.c_int32, c.c_char_p, c.c_int64]
     lib.moonshine_b200_debug_resample.restype = c.c_int64

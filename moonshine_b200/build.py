@@ -69,13 +69,15 @@ def build(force: bool = False, verbose: bool = True) -> str:
     link_stamp = LIB + ".link"
     link_cmd_id = "soname-v1"
     if procs or force or not os.path.exists(LIB) or not os.path.exists(link_stamp) or open(link_stamp).read() != link_cmd_id:
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+        tmp = LIB + ".tmp"  # link beside, then rename: a snapshot taken mid-build never sees a half-written library
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                       "-lcudart", "-Xlinker", "--no-undefined",
                                                       # SONAME = the name every reference binding dlopens
                                                       "-Xlinker", "-soname=libmoonshine.so"]
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(tmp, LIB)
         with open(link_stamp, "w") as f:
             f.write(link_cmd_id)
     return LIB

@@ -532,6 +532,33 @@ int32_t moonshine_b200_debug_biaser_apply(const int32_t* seqs, const int32_t* se
   }
 }
 
+// The same through the sparse form the on-device path uploads: dense root bonuses + per-step (token, delta) pairs.
+int32_t moonshine_b200_debug_biaser_apply_sparse(const int32_t* seqs, const int32_t* seq_lens, int32_t n_seqs, float boost,
+                                                 const int32_t* path, int32_t n_path, float* logits, int32_t vocab) {
+  try {
+    KeytermBiaser b;
+    b.set_boost(boost);
+    size_t o = 0;
+    for (int32_t i = 0; i < n_seqs; i++) {
+      b.add_token_sequence(std::vector<int32_t>(seqs + o, seqs + o + seq_lens[i]));
+      o += (size_t)seq_lens[i];
+    }
+    KeytermBiaser::Walk w;
+    for (int32_t i = 0; i < n_path; i++) b.advance(w, path[i]);
+    const std::vector<float> shared = b.root_bonus(vocab);
+    std::vector<std::pair<int32_t, float>> extra;
+    b.step_bonus(w, vocab, extra);
+    std::vector<float> bonus(shared);
+    for (const auto& e : extra) bonus[(size_t)e.first] += e.second;
+    for (int32_t v = 0; v < vocab; v++)
+      if (bonus[(size_t)v] != 0.0f) logits[v] += bonus[(size_t)v];
+    return MOONSHINE_ERROR_NONE;
+  } catch (const std::exception& e) {
+    MSB_LOGF("debug_biaser_apply_sparse failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+}
+
 // key terms of a passage, NUL-separated; returns the term count
 int32_t moonshine_b200_debug_extract_terms(const uint8_t* tokenizer, uint64_t tokenizer_size, const char* context,
                                            int32_t max_terms, char* out, int64_t cap) {

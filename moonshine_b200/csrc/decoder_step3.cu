@@ -45,6 +45,7 @@ constexpr int kStageBytes = 32768;
 constexpr int kMaxNB = 16;                       // utterances per attention job (one N = 16 MMA operand)
 constexpr int kMaxPairs = 8;                     // float2 per lane of a LayerNorm row: D <= 512
 constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM cycles
+constexpr int kBiasEntries = 512;                // per-utterance bias entries that may fall into one vocab chunk per pass
 
 enum { PH_SELF = 0, PH_CROSS, PH_OC, PH_FC1, PH_FC2, PH_FINAL, PH_LOGITS, PH_KINDS };
 constexpr int kPhasesPerLayer = 5;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void produce_block_f16(Ring& ring, const __half* M, i
 
 // ---- shared memory layout ----
 struct SmemLayout3 {
-  int bars, active, flags, rope, argv, argi, scratch, ring;  // byte offsets
+  int bars, active, flags, rope, argv, argi, sbias, rowflag, ent_key, ent_val, ent_n, scratch, ring;  // byte offsets
   int xp, act, att, sc, ps, red;                             // attention-job scratch (inside `scratch`)
   int actw, attw, nxl, ns, total;
 };
@@ -275,6 +276,11 @@ __host__ __device__ inline SmemLayout3 smem_layout3(int B, int D, int hd, int Kc
   L.rope = take(128 * 4);
   L.argv = take(kWarpsC * 64 * 4);
   L.argi = take(kWarpsC * 64 * 4);
+  L.sbias = take(256 * 4);            // logit bias: static bonuses of this CTA's vocab chunk,
+  L.rowflag = take(256);              // rows with a per-utterance entry,
+  L.ent_key = take(kBiasEntries * 4); // (row << 8 | utterance column) of each entry that falls into the chunk,
+  L.ent_val = take(kBiasEntries * 4); // its bonus,
+  L.ent_n = take(16);                 // and their count
   o = (o + 1023) / 1024 * 1024;
   L.scratch = o;
   L.actw = 3 * hd;
@@ -315,6 +321,9 @@ struct Ctx {
   int prof_n;
   float *act, *att, *red, *ps, *sc, *argv;
   int *flags, *argi;
+  float *sbias, *ent_val;       // logit bias tables (logits phase)
+  unsigned char* rowflag;
+  int *ent_key, *ent_n;
   const unsigned char* active;  // [B] 1 = utterance still decoding at kernel start
   int actw, attw;
 };
@@ -1145,6 +1154,36 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
   for (int b0 = 0; b0 < p.B; b0 += nx) {
     const int nb = min(nx, p.B - b0);
     planes_from_rows(xp, nx, p.xfin, D, b0, nb, 0, D, c.active);
+    const bool biased = p.bias_static != nullptr || p.bias_dyn_n != nullptr;
+    if (biased) {
+      // bonuses that land in this CTA's vocab chunk: the shared ones as a dense slice, the per-utterance ones as
+      // (row, utterance column, bonus) entries
+      for (int i = threadIdx.x; i < 256; i += kConsumers) {
+        const int v = item * VC + i;
+        c.sbias[i] = (p.bias_static != nullptr && i < VC && v < V) ? __ldg(p.bias_static + v) : 0.f;
+        c.rowflag[i] = 0;
+      }
+      if (threadIdx.x == 0) *c.ent_n = 0;
+      csync();
+      if (p.bias_dyn_n != nullptr) {
+        const int cap = p.bias_dyn_cap;
+        for (int idx = threadIdx.x; idx < nb * cap; idx += kConsumers) {
+          const int b = idx / cap, k = idx - b * cap;
+          if (k < p.bias_dyn_n[b0 + b]) {
+            const int loc = p.bias_dyn_ids[(int64_t)(b0 + b) * cap + k] - item * VC;
+            if (loc >= 0 && loc < VC) {
+              const int slot = atomicAdd(c.ent_n, 1);
+              if (slot >= kBiasEntries) atomicExch(c.err, 2u);  // table overflow: fail the decode, never drop a bonus
+              if (slot < kBiasEntries) {
+                c.ent_key[slot] = (loc << 8) | b;
+                c.ent_val[slot] = p.bias_dyn_val[(int64_t)(b0 + b) * cap + k];
+                c.rowflag[loc] = 1;
+              }
+            }
+          }
+        }
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     csync();
     prof_mark(c, 35);
@@ -1211,6 +1250,24 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      if (biased && vok) {
+        const float sb = c.sbias[vrow];
+#pragma unroll
+        for (int e = 0; e < 16; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + sb);
+        if (c.rowflag[vrow]) {  // rare: some utterance's active key-term path continues with this token
+          const int n_ent = min(*c.ent_n, kBiasEntries);
+          for (int s2 = 0; s2 < n_ent; s2++) {
+            const int key = c.ent_key[s2];
+            const int col = (key & 255) - cb;
+            if ((key >> 8) == vrow && col >= 0 && col < 16) {
+              const float add = c.ent_val[s2];
+#pragma unroll
+              for (int e = 0; e < 16; e++)
+                if (e == col) r[e] = __float_as_uint(__uint_as_float(r[e]) + add);
+            }
+          }
+        }
       }
 #pragma unroll
       for (int e = 0; e < 16; e++) {
@@ -1350,6 +1407,11 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
   c.flags = reinterpret_cast<int*>(smem_raw + L.flags);
   c.argv = reinterpret_cast<float*>(smem_raw + L.argv);
   c.argi = reinterpret_cast<int*>(smem_raw + L.argi);
+  c.sbias = reinterpret_cast<float*>(smem_raw + L.sbias);
+  c.rowflag = smem_raw + L.rowflag;
+  c.ent_key = reinterpret_cast<int*>(smem_raw + L.ent_key);
+  c.ent_val = reinterpret_cast<float*>(smem_raw + L.ent_val);
+  c.ent_n = reinterpret_cast<int*>(smem_raw + L.ent_n);
   c.active = active;
   c.actw = L.actw;
   c.attw = L.attw;
@@ -1450,7 +1512,20 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
   }
 }
 
+__global__ void decoder_resolve_kernel(const __grid_constant__ DecoderParams p, int* out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= p.B) return;
+  const int tok = resolve_token_warp(p, b, p.step & 1);
+  if ((threadIdx.x & 31) == 0) out[b] = tok;
+}
+
 }  // namespace
+
+void launch_decoder_resolve(const DecoderParams& p, int* out, cudaStream_t stream) {
+  const int warps_per_block = 4;
+  const int blocks = (p.B + warps_per_block - 1) / warps_per_block;
+  decoder_resolve_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(p, out);
+}
 
 bool decoder_step3_supported(const DecoderParams& p) {
   return p.D % 32 == 0 && p.D <= 64 * kMaxPairs && p.hd <= 64 && p.hd % 4 == 0 && p.rot_dim <= 128 && p.Tpad <= 1024 &&

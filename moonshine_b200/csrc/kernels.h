@@ -206,6 +206,13 @@ struct DecoderParams {
   float* attc;            // [B][D] cross-attention output (all heads), input of the output projection
   float* act;             // [B][I] silu(gate) * value
   unsigned int* sync3;    // [kSync3Words] epoch, error flag, one completion counter per phase (own 128-byte line)
+  // sparse logit bonuses added in the logits epilogue before the fused argmax (key-term biasing,
+  // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
+  const float* bias_static;   // [V] bonus shared by every utterance and step (the trie root's children)
+  const int* bias_dyn_n;      // [B] per-utterance entries of this step
+  const int* bias_dyn_ids;    // [B][bias_dyn_cap] token ids
+  const float* bias_dyn_val;  // [B][bias_dyn_cap] bonus ON TOP of bias_static[id]
+  int bias_dyn_cap;
 };
 constexpr int kSync3Words = 32 + 32 * 64;
 void launch_decoder_step3(const DecoderParams& p, int grid, cudaStream_t stream);
@@ -213,6 +220,9 @@ size_t decoder_step3_smem_bytes(const DecoderParams& p);
 // fills nb_self / nb_cross / nx / job_first / job_ncta for batch size p.B on a grid of `grid` CTAs
 void decoder_step3_plan(DecoderParams& p, int grid);
 bool decoder_step3_supported(const DecoderParams& p);
+// out[b] = id emitted by the step that was just launched (p.step), resolved from its argmax candidates with the
+// reference's lowest-index tie rule; the next launch's prologue resolves the same value on its own.
+void launch_decoder_resolve(const DecoderParams& p, int* out, cudaStream_t stream);
 void launch_decoder_step(const DecoderParams& p, int grid, cudaStream_t stream);
 // v2: operands streamed through a TMA-bulk smem ring by a producer warp.
 void launch_decoder_step2(const DecoderParams& p, int grid, cudaStream_t stream);

@@ -1035,6 +1035,71 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       launch_step();
       stage("decoder_step", t, 16);
     }
+  } else if (use_v3 && hook->shared_bonus(V) != nullptr) {
+    // On-device biasing (reference: ContextBiaser between decode_step and the argmax, core/transcriber.cpp:1440-1470).
+    // The host only walks the trie: per step it uploads each utterance's few (token, bonus) pairs, the kernel adds
+    // them (and the shared root bonuses) in the logits epilogue before its fused argmax, and B token ids come back
+    // to advance the walks.  No logits cross PCIe.
+    const std::vector<float>& shared = *hook->shared_bonus(V);
+    const int cap = 256;
+    bias_static_dev_.reserve((size_t)V);
+    CUDA_CHECK(cudaMemcpyAsync(bias_static_dev_.ptr, shared.data(), (size_t)V * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    bias_n_dev_.reserve(B); bias_ids_dev_.reserve((size_t)B * cap); bias_val_dev_.reserve((size_t)B * cap);
+    step_tok_dev_.reserve(B);
+    pin_bias_i32_.reserve((size_t)B + (size_t)B * cap + B);
+    pin_bias_f32_.reserve((size_t)B * cap);
+    int* h_n = pin_bias_i32_.ptr;
+    int* h_ids = h_n + B;
+    int* h_tok = h_ids + (size_t)B * cap;
+    float* h_val = pin_bias_f32_.ptr;
+    p.bias_static = bias_static_dev_.ptr;
+    p.bias_dyn_n = bias_n_dev_.ptr; p.bias_dyn_ids = bias_ids_dev_.ptr; p.bias_dyn_val = bias_val_dev_.ptr;
+    p.bias_dyn_cap = cap;
+    std::vector<char> finished(B, 0);
+    hooked_tokens.assign(B, std::vector<int32_t>{(int32_t)d_.bos});
+    int remaining = 0;
+    for (int b = 0; b < B; b++) {
+      finished[b] = mlen[b] <= 0;
+      remaining += finished[b] ? 0 : 1;
+    }
+    std::vector<std::pair<int32_t, float>> pairs;
+    steps_launched = 0;
+    for (int t = 0; t < max_steps && remaining > 0; t++) {
+      for (int b = 0; b < B; b++) {
+        h_n[b] = 0;
+        if (finished[b]) continue;
+        hook->step_bonus(b, pairs);
+        if ((int)pairs.size() > cap) throw std::runtime_error("key-term biasing: more than 256 active continuations for one utterance");
+        h_n[b] = (int)pairs.size();
+        for (size_t k = 0; k < pairs.size(); k++) {
+          h_ids[(size_t)b * cap + k] = pairs[k].first;
+          h_val[(size_t)b * cap + k] = pairs[k].second;
+        }
+      }
+      CUDA_CHECK(cudaMemcpyAsync(bias_n_dev_.ptr, h_n, B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(bias_ids_dev_.ptr, h_ids, (size_t)B * cap * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(bias_val_dev_.ptr, h_val, (size_t)B * cap * sizeof(float), cudaMemcpyHostToDevice, stream_));
+      p.step = t;
+      p.prof = nullptr;
+      p.logits_out = (t < dbg_steps) ? logits_dbg_.ptr + (size_t)t * B * V : nullptr;
+      launch_step();
+      launch_decoder_resolve(p, step_tok_dev_.ptr, stream_);
+      steps_launched++;
+      CUDA_CHECK(cudaMemcpyAsync(h_tok, step_tok_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      for (int b = 0; b < B; b++) {
+        if (finished[b]) continue;
+        const int tok = h_tok[b];
+        hooked_tokens[b].push_back(tok);
+        if (tok == d_.eos || t + 1 >= mlen[b]) {
+          finished[b] = 1;
+          remaining--;
+        }
+        if (tok != d_.eos) hook->advance(b, tok);
+      }
+    }
+    p.logits_out = nullptr;
+    p.bias_static = nullptr; p.bias_dyn_n = nullptr; p.bias_dyn_ids = nullptr; p.bias_dyn_val = nullptr;
   } else {
     // Host-stepped greedy loop: logits of step t come back, the hook edits them, the host's first-max argmax
     // picks the id, and the id enters step t + 1 through the teacher-forcing input (the kernel's own EOS /
@@ -1093,7 +1158,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     std::vector<unsigned long long> h((size_t)grid * 512);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(h.data(), prof_buf.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
-    for (int cta : {0, 1, 77, 127, 140, 147}) {
+    for (int cta : {0, 1, 31, 77, 127, 128, 131, 140, 147}) {
       if (cta >= grid) continue;
       fprintf(stderr, "PROF cta %d:", cta);
       for (int i = 0; i < 512 && h[(size_t)cta * 512 + i]; i++)

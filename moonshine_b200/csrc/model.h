@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "common.h"
@@ -49,6 +50,12 @@ struct LogitHook {
   virtual ~LogitHook() = default;
   virtual void apply(int utterance, float* logits, int vocab) = 0;  // before the argmax of every step
   virtual void advance(int utterance, int token) = 0;               // after a non-EOS id was emitted
+  // Sparse form, used by the on-device path (v3 kernel: the bonuses are added in the logits epilogue before the
+  // fused argmax, nothing but B token ids crosses PCIe per step).  shared_bonus: the bonuses that hold for every
+  // utterance at every step as a dense [vocab] array (nullptr = this hook has no sparse form: host-stepped path);
+  // step_bonus: this step's extra bonuses of one utterance, ON TOP of the shared ones, as (token id, bonus).
+  virtual const std::vector<float>* shared_bonus(int vocab) { (void)vocab; return nullptr; }
+  virtual void step_bonus(int utterance, std::vector<std::pair<int32_t, float>>& out) { (void)utterance; out.clear(); }
 };
 
 struct StageTimes {
@@ -147,7 +154,10 @@ class Model {
   DeviceBuffer<int> meta_i32_;       // packed int32 metadata
   DeviceBuffer<int64_t> meta_i64_;   // packed int64 metadata
   DeviceBuffer<unsigned int> barrier_, sync3_;
-  DeviceBuffer<float> attc_, act_;
+  DeviceBuffer<float> attc_, act_, bias_static_dev_, bias_val_dev_;
+  DeviceBuffer<int> bias_n_dev_, bias_ids_dev_, step_tok_dev_;
+  PinnedBuffer<int> pin_bias_i32_;
+  PinnedBuffer<float> pin_bias_f32_;
   DeviceBuffer<int> nactive_;
   PinnedBuffer<int> pin_i32_;
   PinnedBuffer<int64_t> pin_i64_;

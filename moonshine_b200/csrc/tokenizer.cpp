@@ -316,6 +316,47 @@ void KeytermBiaser::apply(const Walk& w, float* logits, int vocab) const {
   for (const auto& pb : pending) logits[pb.first] += pb.second;
 }
 
+std::vector<float> KeytermBiaser::root_bonus(int vocab) const {
+  std::vector<float> out((size_t)vocab, 0.f);
+  if (sequences_ == 0) return out;
+  const float bonus = boost_ * (1.0f + std::log(1.0f));  // depth 1
+  for (const auto& child : nodes_[0].children)
+    if (child.first >= 0 && child.first < vocab) out[(size_t)child.first] = bonus;
+  return out;
+}
+
+void KeytermBiaser::step_bonus(const Walk& w, int vocab, std::vector<std::pair<int32_t, float>>& out) const {
+  out.clear();
+  if (sequences_ == 0) return;
+  for (int32_t node_index : w.active) {
+    if (node_index == 0) continue;  // the root's children are the shared part
+    const Node& node = nodes_[(size_t)node_index];
+    const float bonus = boost_ * (1.0f + std::log((float)(node.depth + 1)));
+    for (const auto& child : node.children) {
+      const int32_t tok = child.first;
+      if (tok < 0 || tok >= vocab) continue;
+      bool merged = false;
+      for (auto& pb : out) {
+        if (pb.first == tok) {
+          pb.second = std::max(pb.second, bonus);
+          merged = true;
+          break;
+        }
+      }
+      if (!merged) out.emplace_back(tok, bonus);
+    }
+  }
+  // merged bonus -> what it adds on top of the root's share of the same token (apply() keeps the largest)
+  const float root = boost_ * (1.0f + std::log(1.0f));
+  size_t keep = 0;
+  for (auto& pb : out) {
+    const bool root_child = nodes_[0].children.find(pb.first) != nodes_[0].children.end();
+    const float delta = root_child ? std::max(pb.second, root) - root : pb.second;
+    if (delta != 0.0f) out[keep++] = {pb.first, delta};
+  }
+  out.resize(keep);
+}
+
 void KeytermBiaser::advance(Walk& w, int32_t token) const {
   if (sequences_ == 0) return;
   std::vector<int32_t> next{0};  // the root stays active: a term can start at any token

@@ -5,6 +5,7 @@
 #include <unordered_map>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace msb {
@@ -56,6 +57,11 @@ class KeytermBiaser {
   };
   void apply(const Walk& w, float* logits, int vocab) const;
   void advance(Walk& w, int32_t token) const;
+  // The same bonuses in sparse form (on-device biasing): the root is always active, so its children's bonus holds
+  // for every utterance at every step (dense [vocab]); the deeper active nodes of a walk add, per token, the
+  // difference between the merged (largest) bonus apply() would use and the root's share.
+  std::vector<float> root_bonus(int vocab) const;
+  void step_bonus(const Walk& w, int vocab, std::vector<std::pair<int32_t, float>>& out) const;
 
  private:
   struct Node {

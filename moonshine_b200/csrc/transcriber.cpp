@@ -422,6 +422,16 @@ struct BatchBiasHook : LogitHook {
   BatchBiasHook(const KeytermBiaser& b, size_t n) : biaser(b), walks(n) {}
   void apply(int u, float* logits, int vocab) override { biaser.apply(walks[(size_t)u], logits, vocab); }
   void advance(int u, int token) override { biaser.advance(walks[(size_t)u], token); }
+  std::vector<float> shared;
+  int vocab_ = 0;
+  const std::vector<float>* shared_bonus(int vocab) override {
+    if (shared.size() != (size_t)vocab) shared = biaser.root_bonus(vocab);
+    vocab_ = vocab;
+    return &shared;
+  }
+  void step_bonus(int u, std::vector<std::pair<int32_t, float>>& out) override {
+    biaser.step_bonus(walks[(size_t)u], vocab_, out);
+  }
 };
 }  // namespace
 

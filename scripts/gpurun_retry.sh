@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh <timeout_s> '<command>'   -- resubmits while the pod answers "busy" (exit 3, nothing charged)
+T=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  echo "[retry] pod busy, attempt $i; sleeping 45 s"
+  sleep 45
+done
+exit 3

@@ -203,12 +203,20 @@ def test_keyterm_biaser_matches_reference_code(ref, product):
             ref.ref_biaser_advance(b, int(t))
         lr = rng.standard_normal(vocab).astype(np.float32)
         lp = lr.copy()
+        lr0 = lr.copy()
         ref.ref_biaser_apply(b, _f32(lr), vocab)
         ref.ref_biaser_free(b)
         rc = product.moonshine_b200_debug_biaser_apply(_i32(flat), _i32(lens), len(seqs), 2.0, _i32(path), len(path),
                                                        _f32(lp), vocab)
         assert rc == 0
         np.testing.assert_array_equal(lp, lr)
+        # the sparse form the GPU path uploads (shared root bonuses + this step's per-token extras) adds up to the same
+        ls = lr0.copy()
+        rc = product.moonshine_b200_debug_biaser_apply_sparse(_i32(flat), _i32(lens), len(seqs), 2.0, _i32(path), len(path),
+                                                              _f32(ls), vocab)
+        assert rc == 0
+        np.testing.assert_allclose(ls, lr, rtol=0, atol=1e-6)
+        assert np.array_equal(ls != lr0, lr != lr0)   # exactly the same tokens are touched
 
 
 PASSAGE = """It was the best of times at Tellson’s Bank — Tellson's, by Temple Bar, was an old-fashioned place.
