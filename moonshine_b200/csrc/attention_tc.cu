@@ -74,6 +74,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp (tcgen05.mma wants uniform-register operands: issued under elect.sync inside
+// warp-uniform control flow it is a few instructions; from a divergent `if (tid == X)` the compiler wraps every
+// MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop, ~95 ns per MMA measured on B200).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -191,23 +205,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
   const uint32_t tmem = tmem_base_smem;
   uint32_t bar_phase = 0;
 
-  // ---- S = Q K^T into TMEM columns [0, Tk) ----
-  if (threadIdx.x == 0) {
-    for (int n0 = 0; n0 < Tk; n0 += 256) {
-      const int nc = min(256, Tk - n0);
-      const uint32_t idesc = idesc_for(nc);
-      for (int ks = 0; ks < ksteps; ks++) {
-        const int kb = ks >> 1;
-        const uint32_t ko = (uint32_t)(ks & 1) * 32u;
-        const uint32_t a_hi = smem_u32(Qs + (size_t)kb * 2 * 128 * 64) + ko, a_lo = a_hi + 128 * 64;
-        const uint32_t b_hi = smem_u32(KP + (size_t)kb * 2 * Tk * 64) + (uint32_t)n0 * 64u + ko;
-        const uint32_t b_lo = b_hi + (uint32_t)Tk * 64u;
-        umma_bf16(tmem + n0, make_desc_sw64(a_lo), make_desc_sw64(b_hi), idesc, ks ? 1u : 0u);
-        umma_bf16(tmem + n0, make_desc_sw64(a_hi), make_desc_sw64(b_lo), idesc, 1u);
-        umma_bf16(tmem + n0, make_desc_sw64(a_hi), make_desc_sw64(b_hi), idesc, 1u);
+  // ---- S = Q K^T into TMEM columns [0, Tk) ----  (warp 0, one elected lane, operands made provably uniform)
+  const int warp_u = (int)uniform_u32(threadIdx.x >> 5);
+  const uint32_t tmem_u = uniform_u32(tmem);
+  const uint32_t qs_u = uniform_u32(smem_u32(Qs)), kp_u = uniform_u32(smem_u32(KP));
+  if (warp_u == 0) {
+    if (elect_one()) {
+      for (int n0 = 0; n0 < Tk; n0 += 256) {
+        const int nc = min(256, Tk - n0);
+        const uint32_t idesc = idesc_for(nc);
+        for (int ks = 0; ks < ksteps; ks++) {
+          const int kb = ks >> 1;
+          const uint32_t ko = (uint32_t)(ks & 1) * 32u;
+          const uint32_t a_hi = qs_u + (uint32_t)(kb * 2 * 128 * 64) + ko, a_lo = a_hi + 128 * 64;
+          const uint32_t b_hi = kp_u + (uint32_t)(kb * 2 * Tk * 64) + (uint32_t)n0 * 64u + ko;
+          const uint32_t b_lo = b_hi + (uint32_t)Tk * 64u;
+          umma_bf16(tmem_u + n0, make_desc_sw64(a_lo), make_desc_sw64(b_hi), idesc, ks ? 1u : 0u);
+          umma_bf16(tmem_u + n0, make_desc_sw64(a_hi), make_desc_sw64(b_lo), idesc, 1u);
+          umma_bf16(tmem_u + n0, make_desc_sw64(a_hi), make_desc_sw64(b_hi), idesc, 1u);
+        }
       }
+      umma_commit(&mma_bar);
     }
-    umma_commit(&mma_bar);
+    __syncwarp();
   }
   mbar_wait(&mma_bar, bar_phase & 1);
   bar_phase++;
@@ -369,20 +389,25 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp_u == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int steps = rk >> 4;  // k16 steps with data
-      for (int s = 0; s < steps; s++) {
-        const int kblock = s >> 1;
-        const uint32_t ko = (uint32_t)(s & 1) * 32u;
-        const uint32_t a_hi = smem_u32(KP + (size_t)kblock * 2 * 128 * 64) + ko, a_lo = a_hi + 128 * 64;
-        const uint32_t b_hi = smem_u32(Vs + (size_t)kblock * 2 * NV * 64) + ko, b_lo = b_hi + NV * 64;
-        const uint32_t acc = (round | s) ? 1u : 0u;
-        umma_bf16(tmem + kOCol, make_desc_sw64(a_lo), make_desc_sw64(b_hi), idesc_pv, acc);
-        umma_bf16(tmem + kOCol, make_desc_sw64(a_hi), make_desc_sw64(b_lo), idesc_pv, 1u);
-        umma_bf16(tmem + kOCol, make_desc_sw64(a_hi), make_desc_sw64(b_hi), idesc_pv, 1u);
+      const uint32_t vs_u = uniform_u32(smem_u32(Vs));
+      const int steps = (int)uniform_u32((uint32_t)(rk >> 4));  // k16 steps with data
+      const uint32_t round_u = uniform_u32((uint32_t)round);
+      if (elect_one()) {
+        for (int s = 0; s < steps; s++) {
+          const int kblock = s >> 1;
+          const uint32_t ko = (uint32_t)(s & 1) * 32u;
+          const uint32_t a_hi = kp_u + (uint32_t)(kblock * 2 * 128 * 64) + ko, a_lo = a_hi + 128 * 64;
+          const uint32_t b_hi = vs_u + (uint32_t)(kblock * 2 * NV * 64) + ko, b_lo = b_hi + NV * 64;
+          const uint32_t acc = (round_u | (uint32_t)s) ? 1u : 0u;
+          umma_bf16(tmem_u + kOCol, make_desc_sw64(a_lo), make_desc_sw64(b_hi), idesc_pv, acc);
+          umma_bf16(tmem_u + kOCol, make_desc_sw64(a_hi), make_desc_sw64(b_lo), idesc_pv, 1u);
+          umma_bf16(tmem_u + kOCol, make_desc_sw64(a_hi), make_desc_sw64(b_hi), idesc_pv, 1u);
+        }
+        umma_commit(&mma_bar);
       }
-      umma_commit(&mma_bar);
+      __syncwarp();
     }
     // the next round overwrites P / V: wait until the tensor core has read them
     mbar_wait(&mma_bar, bar_phase & 1);

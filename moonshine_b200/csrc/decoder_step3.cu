@@ -45,6 +45,7 @@ constexpr int kStageBytes = 32768;
 constexpr int kMaxNB = 16;                       // utterances per attention job (one N = 16 MMA operand)
 constexpr int kMaxPairs = 8;                     // float2 per lane of a LayerNorm row: D <= 512
 constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM cycles
+constexpr int kPlaneBatch = 6;                   // (row, 8-input) items a thread keeps in flight in planes_from_rows
 constexpr int kBiasEntries = 512;                // per-utterance bias entries that may fall into one vocab chunk per pass
 
 enum { PH_SELF = 0, PH_CROSS, PH_OC, PH_FC1, PH_FC2, PH_FINAL, PH_LOGITS, PH_KINDS };
@@ -67,6 +68,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Data another CTA produced during this launch.  The consumer's dependency wait is an ld.acquire.gpu poll, which
+// ptxas turns into LDG.STRONG.GPU + CCTL.IVALL: the SM's L1 holds nothing stale once the wait is over, so these are
+// ordinary (weak, L1-allocating) loads the compiler may batch freely.  (ld.global.cg would compile to ORDERED
+// LDG.STRONG.GPU loads: measured 2.4-2.9 us for one row's 10-30 loads.)
+template <typename T>
+__device__ __forceinline__ T ld_fresh(const T* p) { return *p; }
 __device__ __forceinline__ bool poisoned(const unsigned* err) { return *reinterpret_cast<const volatile unsigned*>(err) != 0u; }
 
 // ---- mbarrier / bulk-copy primitives (PTX) ----
@@ -146,6 +153,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a converged warp.  tcgen05.mma takes its operands from UNIFORM registers: issued under elect.sync
+// inside warp-uniform control flow, with operands the compiler can prove uniform (shuffle broadcasts), it is a
+// handful of instructions; issued from a divergent `if (threadIdx.x == 0)` the compiler wraps EVERY MMA in a
+// waterfall loop (ELECT / 5x R2UR.BROADCAST / BRA.U.ANY), measured ~95 ns per MMA on B200.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t idesc_bf16(int n) {  // D fp32, A/B bf16 K-major, M = 128, N = n
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
@@ -315,6 +336,7 @@ struct Ctx {
   unsigned char* xp;         // smem: x planes of an attention job (16 rows)
   unsigned char* xg;         // smem: x planes of a GEMM job / logits pass (aliases the attention scratch)
   uint32_t tmem;             // TMEM base (256 columns)
+  int mma3;                  // experiment: 3 MMAs of N = NXp per k16 step instead of 2 (N = 2 NXp, NXp)
   uint64_t* acc_bar;         // accumulator-ready mbarrier
   int acc_phase;
   unsigned long long* prof;  // optional [grid][kProfSlots] stamps (thread 0)
@@ -351,21 +373,34 @@ struct RowVals {
 };
 __device__ __forceinline__ void row_resolve(RowVals& rv, int D, const float* hrow, const float* part_row, int64_t pstride,
                                             int nparts, const float* __restrict__ bias) {
+  // ld.global.cg compiles to an ORDERED load (LDG.STRONG.GPU) that the compiler never hoists over the adds of the
+  // previous array, and one L2 round trip costs ~0.65 us here: stage up to 4 arrays (20-28 loads per lane) in
+  // registers before the first add, so a row costs 1-2 round trips instead of one per array.  Sum order unchanged.
   const int lane = threadIdx.x & 31;
+  float2 q[4][kMaxPairs];
 #pragma unroll
   for (int i = 0; i < kMaxPairs; i++) {
     const int k = 2 * lane + 64 * i;
-    rv.v[i] = (k < D) ? __ldcg(reinterpret_cast<const float2*>(hrow + k)) : make_float2(0.f, 0.f);
+    rv.v[i] = (k < D) ? ld_fresh(reinterpret_cast<const float2*>(hrow + k)) : make_float2(0.f, 0.f);
   }
-#pragma unroll 4
-  for (int j = 0; j < nparts; j++) {
+  for (int j0 = 0; j0 < nparts; j0 += 4) {
 #pragma unroll
-    for (int i = 0; i < kMaxPairs; i++) {
-      const int k = 2 * lane + 64 * i;
-      if (k < D) {
-        const float2 q = __ldcg(reinterpret_cast<const float2*>(part_row + (int64_t)j * pstride + k));
-        rv.v[i].x += q.x;
-        rv.v[i].y += q.y;
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < kMaxPairs; i++) {
+        const int k = 2 * lane + 64 * i;
+        q[u][i] = (j0 + u < nparts && k < D) ? ld_fresh(reinterpret_cast<const float2*>(part_row + (int64_t)(j0 + u) * pstride + k))
+                                             : make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j0 + u < nparts) {
+#pragma unroll
+        for (int i = 0; i < kMaxPairs; i++) {
+          rv.v[i].x += q[u][i].x;
+          rv.v[i].y += q[u][i].y;
+        }
       }
     }
   }
@@ -374,9 +409,9 @@ __device__ __forceinline__ void row_resolve(RowVals& rv, int D, const float* hro
     for (int i = 0; i < kMaxPairs; i++) {
       const int k = 2 * lane + 64 * i;
       if (k < D) {
-        const float2 q = __ldg(reinterpret_cast<const float2*>(bias + k));
-        rv.v[i].x += q.x;
-        rv.v[i].y += q.y;
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + k));
+        rv.v[i].x += b2.x;
+        rv.v[i].y += b2.y;
       }
     }
   }
@@ -427,27 +462,28 @@ __device__ __forceinline__ void row_to_planes(const RowVals& rv, int D, unsigned
 }
 
 // Activation tile from a plain fp32 matrix: rows [g0, g0 + nb) x columns [k0, k0 + K) of src (row stride ld) ->
-// planes of NXp rows (rows >= nb and inactive rows are zero).  Item = (row, 8 inputs); loads batched 4 deep.
+// planes of NXp rows (rows >= nb and inactive rows are zero).  Item = (row, 8 inputs); loads batched 6 deep (one L2
+// round trip for a 32 x 288 tile).
 __device__ __forceinline__ void planes_from_rows(unsigned char* planes, int NXp, const float* src, int64_t ld, int g0, int nb,
                                                  int k0, int K, const unsigned char* active) {
   const int k8n = (K + 31) / 32 * 4;  // 8-wide chunks per row, whole k-blocks
   const int nitems = NXp * k8n;
-  for (int i0 = threadIdx.x; i0 < nitems; i0 += 4 * kConsumers) {
-    float4 va[4], vb[4];
+  for (int i0 = threadIdx.x; i0 < nitems; i0 += kPlaneBatch * kConsumers) {
+    float4 va[kPlaneBatch], vb[kPlaneBatch];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kPlaneBatch; u++) {
       const int i = i0 + u * kConsumers;
       const int r = i / k8n, k8 = i - r * k8n;
       va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       vb[u] = va[u];
       if (i < nitems && r < nb && active[g0 + r]) {
         const float* s = src + (int64_t)(g0 + r) * ld + k0 + k8 * 8;
-        if (k8 * 8 < K) va[u] = __ldcg(reinterpret_cast<const float4*>(s));
-        if (k8 * 8 + 4 < K) vb[u] = __ldcg(reinterpret_cast<const float4*>(s + 4));
+        if (k8 * 8 < K) va[u] = ld_fresh(reinterpret_cast<const float4*>(s));
+        if (k8 * 8 + 4 < K) vb[u] = ld_fresh(reinterpret_cast<const float4*>(s + 4));
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kPlaneBatch; u++) {
       const int i = i0 + u * kConsumers;
       if (i >= nitems) break;
       const int r = i / k8n, k8 = i - r * k8n;
@@ -476,37 +512,59 @@ __device__ __forceinline__ void gemm_block(Ring& ring, Ctx& c, const unsigned ch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // x planes (generic-proxy stores) -> tensor core
   csync();
-  const uint32_t idesc = idesc_bf16(NXp);
-  if (threadIdx.x == 0) {
+  prof_mark(c, 63);
+  // Two MMAs per k16 step instead of three: the hi and lo planes of the x tile lie back to back ([hi NXp rows |
+  // lo NXp rows], same 64-byte row pitch), so ONE instruction with N = 2 NXp multiplies the weight's hi plane with
+  // both -- columns [0, NXp) = hi.hi, [NXp, 2 NXp) = hi.lo -- and a second with N = NXp adds lo.hi in columns
+  // [2 NXp, 3 NXp).  A small tcgen05.mma costs ~43 ns whatever N is, so this is a third off the GEMV.
+  const uint32_t idesc = idesc_bf16(NXp), idesc2 = idesc_bf16(2 * NXp);
+  const int warp_u = (int)uniform_u32((uint32_t)warp);
+  if (warp_u == 0) {
+    // the whole of warp 0 walks the chunk list in lock step; one elected lane issues the MMAs and the commits
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t xb = smem_u32(xplanes);
+    const uint32_t xb = uniform_u32(smem_u32(xplanes));
+    const uint32_t tm = uniform_u32(c.tmem);
     for (int mt = 0; mt < n_mt; mt++) {
       const int Rp = plane_rows(N, mt), kbc = plane_kb_per_chunk(Rp);
-      const uint32_t tmem_d = c.tmem + (uint32_t)(mt * 3 * NXp);
+      const uint32_t tmem_d = tm + (uint32_t)(mt * 3 * NXp);
       for (int kb0 = 0; kb0 < nkb; kb0 += kbc) {
         const int n = min(kbc, nkb - kb0);
         mbar_wait(&ring.full[ring.stage()], ring.parity(), c.err);
+        __syncwarp();
+        if (kb0 == 0 && mt == 0) prof_mark(c, 74);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = smem_u32(ring.data + (size_t)ring.stage() * kStageBytes);
-        for (int q = 0; q < n; q++) {
-          const int kb = kb0 + q;
-          const uint32_t a_hi = a_base + (uint32_t)(q * Rp * 128), a_lo = a_hi + (uint32_t)(Rp * 64);
-          const uint32_t b_hi = xb + (uint32_t)(kb * NXp * 128), b_lo = b_hi + (uint32_t)(NXp * 64);
+        const uint32_t a_base = uniform_u32(smem_u32(ring.data + (size_t)ring.stage() * kStageBytes));
+        const uint32_t empty_bar = uniform_u32(smem_u32(&ring.empty[ring.stage()]));
+        if (elect_one()) {
+          for (int q = 0; q < n; q++) {
+            const int kb = kb0 + q;
+            const uint32_t a_hi = a_base + (uint32_t)(q * Rp * 128), a_lo = a_hi + (uint32_t)(Rp * 64);
+            const uint32_t b_hi = xb + (uint32_t)(kb * NXp * 128);
 #pragma unroll
-          for (int ks = 0; ks < 2; ks++) {
-            if (kb * 32 + ks * 16 >= K) break;  // nothing but zero padding beyond K
-            const uint32_t ko = (uint32_t)ks * 32u;
-            const uint32_t acc = (kb | ks) ? 1u : 0u;
-            umma_bf16(tmem_d, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, acc);
-            umma_bf16(tmem_d + NXp, make_desc_sw64(a_hi + ko), make_desc_sw64(b_lo + ko), idesc, acc);
-            umma_bf16(tmem_d + 2 * NXp, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+            for (int ks = 0; ks < 2; ks++) {
+              if (kb * 32 + ks * 16 >= K) break;  // nothing but zero padding beyond K
+              const uint32_t ko = (uint32_t)ks * 32u;
+              const uint32_t acc = (kb | ks) ? 1u : 0u;
+              if (c.mma3) {  // experiment knob (MOONSHINE_B200_DECODER_GEMV=mma3): three N = NXp products
+                umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+                umma_bf16(tmem_d + NXp, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + (uint32_t)(NXp * 64) + ko), idesc, acc);
+                umma_bf16(tmem_d + 2 * NXp, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+              } else {
+                umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc2, acc);
+                umma_bf16(tmem_d + 2 * NXp, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, acc);
+              }
+            }
           }
+          // warp 0's arrival on the stage: it is free once the MMAs have read it
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar) : "memory");
         }
-        umma_commit(&ring.empty[ring.stage()]);  // warp 0's arrival: the stage is free once the MMAs have read it
+        __syncwarp();
         ring.advance();
       }
     }
-    umma_commit(c.acc_bar);
+    if (elect_one()) umma_commit(c.acc_bar);
+    __syncwarp();
+    prof_mark(c, 64);
   } else {
     // the empty barriers count one arrival per consumer warp: lane 0 of warps 1-7 gives its own as soon as the
     // chunk has landed (waiting for `full` keeps an arrival from slipping into the stage's previous round)
@@ -515,7 +573,7 @@ __device__ __forceinline__ void gemm_block(Ring& ring, Ctx& c, const unsigned ch
       const int kbc = plane_kb_per_chunk(plane_rows(N, mt));
       total += (nkb + kbc - 1) / kbc;
     }
-    if (lane == 0 && warp != 0) {
+    if (lane == 0) {
       for (int i = 0; i < total; i++) {
         mbar_wait_relaxed(&ring.full[ring.stage()], ring.parity(), c.err);
         mbar_arrive(&ring.empty[ring.stage()]);
@@ -529,6 +587,7 @@ __device__ __forceinline__ void gemm_block(Ring& ring, Ctx& c, const unsigned ch
   mbar_wait_relaxed(c.acc_bar, (uint32_t)(c.acc_phase & 1), c.err);
   c.acc_phase++;
   __syncwarp();
+  prof_mark(c, 65);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int ncb = NXp >> 4;
   for (int u = warp >> 2; u < n_mt * ncb; u += 2) {  // warps 0-3 take the even (m-tile, column block) units, 4-7 the odd
@@ -549,8 +608,8 @@ __device__ __forceinline__ void gemm_block(Ring& ring, Ctx& c, const unsigned ch
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     float v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++)  // small cross terms first, then the hi * hi product
-      v[e] = (__uint_as_float(r[0][e]) + __uint_as_float(r[1][e])) + __uint_as_float(r[2][e]);
+    for (int e = 0; e < 16; e++)  // small cross terms (hi.lo, lo.hi) first, then the hi * hi product
+      v[e] = (__uint_as_float(r[1][e]) + __uint_as_float(r[2][e])) + __uint_as_float(r[0][e]);
     f(mt * 128 + (warp & 3) * 32 + lane, cb, v);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -633,15 +692,65 @@ __device__ __forceinline__ void produce_self(const DecoderParams& p, int l, int 
   if (!tile_active(p, active, nb, b0)) return;
   const DecLayerWeights& w = p.layers[l];
   produce_block_planes(ring, w.wqkvP + (size_t)h * plane_block_bytes(3 * hd, D), 3 * hd, D);
-  if (p.step > 0) {
+  // The self K/V prefix is read straight from global by the warp that owns the utterance (a few KB per item,
+  // written by earlier launches -- walking it through the CTA-wide ring serialised the 8 warps).  It has left L2
+  // since (one step streams more than L2 holds): ask L2 for it now, a phase ahead of its use.
+  if (p.step > 0 && ring.turn == 0) {
     for (int b = 0; b < nb; b++) {
       if (b0 + b >= p.B || !active[b0 + b]) continue;
       const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
-      produce_block_f32(ring, p.ks + bh * hd * p.Smax, hd, p.Smax);   // K^T [hd][Smax]
-      produce_block_f32(ring, p.vs + bh * p.Smax * hd, p.step, hd);   // V rows [0, step)
+      const float* kt = p.ks + bh * hd * p.Smax;
+      const float* vr = p.vs + bh * p.Smax * hd;
+      const uint32_t kbytes = (uint32_t)(hd * p.Smax * 4), vbytes = (uint32_t)((p.step * hd * 4 + 15) & ~15);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kt), "r"(kbytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vr), "r"(vbytes) : "memory");
     }
   }
   produce_block_f32(ring, w.wo + (int64_t)h * hd * D, hd, D);
+}
+
+// per-head partial output projection: dst[b0 + b][:] = att[b][0:hd] . Wo_h[hd][D] (k-major fp32 rows through the ring);
+// thread = (row group g, 4 output features), NJ rows per thread
+template <int NJ>
+__device__ __forceinline__ void o_partial(const DecoderParams& p, Ctx& c, Ring& ring, int nb, int b0, float* dst) {
+  const int D = p.D, hd = p.hd, attw = c.attw;
+  const int D4 = D >> 2;
+  const int G = kConsumers / D4;
+  const int n4 = threadIdx.x % D4, g = threadIdx.x / D4;
+  const bool on = g < G;
+  float acc[NJ][4];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const int rpc = rows_per_chunk_f32(hd, D);
+  for (int k0 = 0; k0 < hd; k0 += rpc) {
+    const int rows = min(rpc, hd - k0);
+    const float4* W = reinterpret_cast<const float4*>(ring.acquire());
+    prof_mark(c, 69);
+    if (on) {
+#pragma unroll 4
+      for (int r = 0; r < rows; r++) {
+        const float4 w4 = W[r * D4 + n4];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          const int b = g + j * G;
+          const float xv = b < nb ? c.att[b * attw + k0 + r] : 0.f;
+          acc[j][0] = fmaf(xv, w4.x, acc[j][0]);
+          acc[j][1] = fmaf(xv, w4.y, acc[j][1]);
+          acc[j][2] = fmaf(xv, w4.z, acc[j][2]);
+          acc[j][3] = fmaf(xv, w4.w, acc[j][3]);
+        }
+      }
+    }
+    ring.release();
+  }
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int b = g + j * G;
+      if (b < nb && !c.flags[b])
+        *reinterpret_cast<float4*>(dst + (int64_t)(b0 + b) * D + n4 * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    }
+  }
 }
 
 __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& ring, const float* hrd, float* hwr) {
@@ -652,6 +761,7 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int actw = c.actw, attw = c.attw;
   load_flags(p, c, nb, b0, false);
+  prof_mark(c, 60);
   // ---- prologue, one warp per row: token / embedding (layer 0) or residual resolve, LayerNorm, x planes ----
   for (int r = warp; r < kMaxNB; r += kWarpsC) {
     RowVals rv;
@@ -669,8 +779,10 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
         row_resolve(rv, D, hrd + (int64_t)b * D, part_fc2(p) + (int64_t)b * D, (int64_t)p.B * D, p.ffn_ksplit,
                     p.layers[l - 1].b2);
       }
+      prof_mark(c, 61);
       if (h == 0) row_store(rv, D, hwr + (int64_t)b * D);
       row_layernorm(rv, D);
+      prof_mark(c, 62);
     }
     row_to_planes(rv, D, c.xp, 16, r, live);
   }
@@ -707,8 +819,9 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
       p.vs[(bh * p.Smax + p.step) * hd + d] = c.act[b * actw + 2 * hd + d];
     }
   }
-  // causal self-attention: ONE WARP per utterance (round-robin), warp-level syncs only.  Cache chunks arrive in
-  // utterance order; every warp acquires / releases every chunk but only the owner computes on it.
+  // causal self-attention: ONE WARP per utterance (round-robin), warp-level syncs only.  The cached prefix
+  // (positions < step, written by earlier launches) comes straight from global memory: lane t reads K^T[d][t]
+  // (coalesced over t), lane d reads V[t][d] (coalesced over d); position `step` comes from shared memory.
   const float scale = rsqrtf((float)hd);
   {
     float* sc = c.sc + warp * (p.Smax + 4);
@@ -717,111 +830,115 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
       if (c.flags[b]) continue;  // uniform
       const bool mine = (owner == warp);
       owner = (owner + 1) & (kWarpsC - 1);
+      if (!mine) continue;
       const float* q = c.act + b * actw;
       const float* kcur = q + hd;
       const float* vcur = q + 2 * hd;
-      if (mine)
-        for (int t = lane; t <= p.step; t += 32) sc[t] = 0.f;
-      if (p.step > 0) {
-        const int rpc = rows_per_chunk_f32(hd, p.Smax);
-        for (int d0 = 0; d0 < hd; d0 += rpc) {
-          const int nd = min(rpc, hd - d0);
-          const float* Kc = reinterpret_cast<const float*>(ring.acquire());
-          if (mine) {
-            for (int t = lane; t < p.step; t += 32) {
-              float s = sc[t];
-              for (int d = 0; d < nd; d++) s = fmaf(q[d0 + d], Kc[d * p.Smax + t], s);
-              sc[t] = s;
-            }
+      const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+      const float* Kt = p.ks + bh * hd * p.Smax;
+      const float* Vr = p.vs + bh * p.Smax * hd;
+      float mx = -INFINITY;
+      // scores: two key positions per lane, 12 head dims per trip = 24 independent loads in flight per lane (the
+      // chain is memory-latency bound: the prefix was written by earlier launches and has left L2 since)
+      for (int t0 = 0; t0 < p.step; t0 += 64) {
+        const int ta = t0 + lane, tb = t0 + 32 + lane;
+        const bool va = ta < p.step, vb = tb < p.step;
+        float sa = 0.f, sb = 0.f;
+#pragma unroll 1
+        for (int d0 = 0; d0 < hd; d0 += 12) {
+          float ka[12], kb[12];
+#pragma unroll
+          for (int u = 0; u < 12; u++) {
+            const bool in = d0 + u < hd;
+            ka[u] = (va && in) ? __ldg(Kt + (int64_t)(d0 + u) * p.Smax + ta) : 0.f;
+            kb[u] = (vb && in) ? __ldg(Kt + (int64_t)(d0 + u) * p.Smax + tb) : 0.f;
           }
-          ring.release();
+#pragma unroll
+          for (int u = 0; u < 12; u++) {
+            const float qd = d0 + u < hd ? q[d0 + u] : 0.f;
+            sa = fmaf(qd, ka[u], sa);
+            sb = fmaf(qd, kb[u], sb);
+          }
         }
+        if (va) { sa *= scale; sc[ta] = sa; mx = fmaxf(mx, sa); }
+        if (vb) { sb *= scale; sc[tb] = sb; mx = fmaxf(mx, sb); }
       }
-      float inv = 0.f;
-      if (mine) {
+      {
         float s = 0.f;
         for (int d = lane; d < hd; d += 32) s = fmaf(q[d], kcur[d], s);
-        s = warp_sum(s);
+        s = warp_sum(s) * scale;
         if (lane == 0) sc[p.step] = s;
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int t = lane; t <= p.step; t += 32) mx = fmaxf(mx, sc[t] * scale);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int t = lane; t <= p.step; t += 32) {
-          const float e = expf(sc[t] * scale - mx);
-          sc[t] = e;
-          sum += e;
-        }
-        inv = 1.0f / warp_sum(sum);
-        __syncwarp();
+        mx = fmaxf(mx, s);
       }
+      mx = warp_max(mx);
+      __syncwarp();
+      prof_mark(c, 66);
+      float sum = 0.f;
+      for (int t = lane; t <= p.step; t += 32) {
+        const float e = expf(sc[t] - mx);
+        sc[t] = e;
+        sum += e;
+      }
+      const float inv = 1.0f / warp_sum(sum);
+      __syncwarp();
+      prof_mark(c, 67);
       float o0 = 0.f, o1 = 0.f;  // lane owns dims d = lane, lane + 32 (hd <= 64)
-      if (p.step > 0) {
-        const int rpc = rows_per_chunk_f32(p.step, hd);
-        for (int r0 = 0; r0 < p.step; r0 += rpc) {
-          const int nr = min(rpc, p.step - r0);
-          const float* Vc = reinterpret_cast<const float*>(ring.acquire());
-          if (mine) {
-            for (int t = 0; t < nr; t++) {
-              const float pt = sc[r0 + t];
-              if (lane < hd) o0 = fmaf(pt, Vc[t * hd + lane], o0);
-              if (lane + 32 < hd) o1 = fmaf(pt, Vc[t * hd + lane + 32], o1);
-            }
+      {
+        const bool has0 = lane < hd, has1 = lane + 32 < hd;
+        int t = 0;
+#pragma unroll 1
+        for (; t + 16 <= p.step; t += 16) {  // 16 rows (32 loads) per trip
+          float v0[16], v1[16];
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            v0[u] = has0 ? __ldg(Vr + (int64_t)(t + u) * hd + lane) : 0.f;
+            v1[u] = has1 ? __ldg(Vr + (int64_t)(t + u) * hd + lane + 32) : 0.f;
           }
-          ring.release();
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            const float pt = sc[t + u];
+            o0 = fmaf(pt, v0[u], o0);
+            o1 = fmaf(pt, v1[u], o1);
+          }
+        }
+#pragma unroll 1
+        for (; t + 8 <= p.step; t += 8) {  // 8 rows (16 loads) per trip
+          float v0[8], v1[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            v0[u] = has0 ? __ldg(Vr + (int64_t)(t + u) * hd + lane) : 0.f;
+            v1[u] = has1 ? __ldg(Vr + (int64_t)(t + u) * hd + lane + 32) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float pt = sc[t + u];
+            o0 = fmaf(pt, v0[u], o0);
+            o1 = fmaf(pt, v1[u], o1);
+          }
+        }
+        for (; t < p.step; t++) {
+          const float pt = sc[t];
+          if (has0) o0 = fmaf(pt, __ldg(Vr + (int64_t)t * hd + lane), o0);
+          if (has1) o1 = fmaf(pt, __ldg(Vr + (int64_t)t * hd + lane + 32), o1);
         }
       }
-      if (mine) {
-        const float pl = sc[p.step];
-        if (lane < hd) c.att[b * attw + lane] = fmaf(pl, vcur[lane], o0) * inv;
-        if (lane + 32 < hd) c.att[b * attw + lane + 32] = fmaf(pl, vcur[lane + 32], o1) * inv;
-      }
+      const float pl = sc[p.step];
+      if (lane < hd) c.att[b * attw + lane] = fmaf(pl, vcur[lane], o0) * inv;
+      if (lane + 32 < hd) c.att[b * attw + lane + 32] = fmaf(pl, vcur[lane + 32], o1) * inv;
     }
   }
+  prof_mark(c, 68);
   csync();
   prof_mark(c, 3);
   // ---- per-head partial output projection (fp32 SIMT, K = hd): thread = (row group g, 4 features) ----
   {
-    const int D4 = D >> 2;
-    const int G = kConsumers / D4;  // >= 2 for D <= 512
-    const int n4 = threadIdx.x % D4, g = threadIdx.x / D4;
-    const bool on = g < G;
-    float acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    const int rpc = rows_per_chunk_f32(hd, D);
-    for (int k0 = 0; k0 < hd; k0 += rpc) {
-      const int rows = min(rpc, hd - k0);
-      const float4* W = reinterpret_cast<const float4*>(ring.acquire());
-      if (on) {
-#pragma unroll 2
-        for (int r = 0; r < rows; r++) {
-          const float4 w4 = W[r * D4 + n4];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int b = g + j * G;
-            if (b < nb) {
-              const float xv = c.att[b * attw + k0 + r];
-              acc[j][0] = fmaf(xv, w4.x, acc[j][0]);
-              acc[j][1] = fmaf(xv, w4.y, acc[j][1]);
-              acc[j][2] = fmaf(xv, w4.z, acc[j][2]);
-              acc[j][3] = fmaf(xv, w4.w, acc[j][3]);
-            }
-          }
-        }
-      }
-      ring.release();
-    }
-    if (on) {
-      float* dst = part_self(p) + (int64_t)h * p.B * D;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int b = g + j * G;
-        if (b < nb && !c.flags[b])
-          *reinterpret_cast<float4*>(dst + (int64_t)(b0 + b) * D + n4 * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-      }
-    }
+    const int G = kConsumers / (D >> 2);  // >= 2 for D <= 512
+    const int nj = (nb + G - 1) / G;      // rows per thread
+    float* dst = part_self(p) + (int64_t)h * p.B * D;
+    if (nj <= 1) o_partial<1>(p, c, ring, nb, b0, dst);
+    else if (nj <= 2) o_partial<2>(p, c, ring, nb, b0, dst);
+    else if (nj <= 4) o_partial<4>(p, c, ring, nb, b0, dst);
+    else o_partial<8>(p, c, ring, nb, b0, dst);
   }
   csync();
   prof_mark(c, 4);
@@ -923,6 +1040,7 @@ __device__ void job_cross(const DecoderParams& p, int l, int job, Ctx& c, Ring& 
         ring.release();
       }
     }
+    prof_mark(c, 70);
     float inv = 0.f;
     if (mine) {
       float lmax = -INFINITY;
@@ -958,6 +1076,7 @@ __device__ void job_cross(const DecoderParams& p, int l, int job, Ctx& c, Ring& 
         *reinterpret_cast<float4*>(dst) = make_float4(s0 * inv, s1 * inv, s2 * inv, s3 * inv);
       }
     }
+    prof_mark(c, 71);
     // ---- PV over V chunks (rows = time); group thread (g, dq) owns 4 dims of rows g, g+G, ... ----
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const int g = gtid / tpr, dq = gtid - g * tpr;
@@ -983,6 +1102,7 @@ __device__ void job_cross(const DecoderParams& p, int l, int job, Ctx& c, Ring& 
         ring.release();
       }
     }
+    prof_mark(c, 72);
     if (mine) {
       if (g < G) *reinterpret_cast<float4*>(&pv[g * hd + dq * 4]) = make_float4(a0, a1, a2, a3);
       gsync();                                   // (3) PV partials visible
@@ -1060,17 +1180,30 @@ __device__ void job_gemm(const DecoderParams& p, int kind, int l, int job, Ctx& 
   const int warp = threadIdx.x >> 5;
   // ---- x planes ----
   if (kind == PH_FC1) {
-    // LN(h + OC) per row, one warp per row; the first m-tile's job of the group keeps the new residual
-    for (int r = warp; r < NXp; r += kWarpsC) {
-      RowVals rv;
-      const bool live = r < j.nb && c.active[j.g0 + r];
-      if (live) {
-        const int b = j.g0 + r;
-        row_resolve(rv, D, hrd + (int64_t)b * D, part_oc(p) + (int64_t)b * D, 0, 1, nullptr);
-        if (j.mt == 0) row_store(rv, D, hwr + (int64_t)b * D);
-        row_layernorm(rv, D);
+    // LN(h + OC) per row, one warp per row, two rows of a warp in flight (the loads of both are issued before
+    // either reduction); the first m-tile's job of the group keeps the new residual
+    for (int r0 = warp; r0 < NXp; r0 += 2 * kWarpsC) {
+      RowVals rv[2];
+      bool live[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int r = r0 + u * kWarpsC;
+        live[u] = r < j.nb && c.active[j.g0 + r];
+        if (live[u]) {
+          const int b = j.g0 + r;
+          row_resolve(rv[u], D, hrd + (int64_t)b * D, part_oc(p) + (int64_t)b * D, 0, 1, nullptr);
+        }
       }
-      row_to_planes(rv, D, c.xg, NXp, r, live);
+      prof_mark(c, 73);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int r = r0 + u * kWarpsC;
+        if (live[u]) {
+          if (j.mt == 0) row_store(rv[u], D, hwr + (int64_t)(j.g0 + r) * D);
+          row_layernorm(rv[u], D);
+        }
+        if (r < NXp) row_to_planes(rv[u], D, c.xg, NXp, r, live[u]);
+      }
     }
   } else if (kind == PH_OC) {
     planes_from_rows(c.xg, NXp, p.attc, D, j.g0, j.nb, 0, K, c.active);
@@ -1189,33 +1322,42 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
     prof_mark(c, 35);
     int nchunks = 0;
     for (int mt = 0; mt < n_mt; mt++) nchunks += (nkb + 1) >> 1;
-    if (threadIdx.x == 0) {
+    const int warp_u = (int)uniform_u32((uint32_t)warp);
+    if (warp_u == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t xb = uniform_u32(smem_u32(xp));
+      const uint32_t tm = uniform_u32(c.tmem);
       for (int mt = 0; mt < n_mt; mt++) {
         const int R = min(128, VC - mt * 128);
-        const uint32_t tmem_d = c.tmem + (uint32_t)(mt * nx);
+        const uint32_t tmem_d = tm + (uint32_t)(mt * nx);
         for (int kb = 0; kb < nkb; kb += 2) {
           const int n = min(2, nkb - kb);
           mbar_wait(&ring.full[ring.stage()], ring.parity(), c.err);
+          __syncwarp();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_base = smem_u32(ring.data + (size_t)ring.stage() * kStageBytes);
-          for (int q = 0; q < n; q++) {
-            const uint32_t a_hi = a_base + (uint32_t)(q * R * 128), a_lo = a_hi + (uint32_t)(R * 64);
-            const uint32_t b_hi = smem_u32(xp + (size_t)(kb + q) * nx * 128), b_lo = b_hi + (uint32_t)(nx * 64);
+          const uint32_t a_base = uniform_u32(smem_u32(ring.data + (size_t)ring.stage() * kStageBytes));
+          const uint32_t empty_bar = uniform_u32(smem_u32(&ring.empty[ring.stage()]));
+          if (elect_one()) {
+            for (int q = 0; q < n; q++) {
+              const uint32_t a_hi = a_base + (uint32_t)(q * R * 128), a_lo = a_hi + (uint32_t)(R * 64);
+              const uint32_t b_hi = xb + (uint32_t)((kb + q) * nx * 128), b_lo = b_hi + (uint32_t)(nx * 64);
 #pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-              const uint32_t ko = (uint32_t)jj * 32u;
-              const uint32_t first = (kb | q | jj) ? 1u : 0u;
-              umma_bf16(tmem_d, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, first);
-              umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_lo + ko), idesc, 1u);
-              umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, 1u);
+              for (int jj = 0; jj < 2; jj++) {
+                const uint32_t ko = (uint32_t)jj * 32u;
+                const uint32_t first = (kb | q | jj) ? 1u : 0u;
+                umma_bf16(tmem_d, make_desc_sw64(a_lo + ko), make_desc_sw64(b_hi + ko), idesc, first);
+                umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_lo + ko), idesc, 1u);
+                umma_bf16(tmem_d, make_desc_sw64(a_hi + ko), make_desc_sw64(b_hi + ko), idesc, 1u);
+              }
             }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar) : "memory");
           }
-          umma_commit(&ring.empty[ring.stage()]);
+          __syncwarp();
           ring.advance();
         }
       }
-      umma_commit(c.acc_bar);
+      if (elect_one()) umma_commit(c.acc_bar);
+      __syncwarp();
       prof_mark(c, 36);
     } else if (lane == 0) {
       for (int i = 0; i < nchunks; i++) {
@@ -1425,6 +1567,7 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
     c.rope = rope;
   }
   c.tmem = tmem_base;
+  c.mma3 = (int)uniform_u32((uint32_t)(p.mma_gemv == 2));
   c.acc_bar = bars + 32;
   c.acc_phase = 0;
   c.prof = reinterpret_cast<unsigned long long*>(p.prof);
@@ -1469,11 +1612,9 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
       else if (kind == PH_FINAL) job_final(p, j, c, hrd);
       else if (kind == PH_LOGITS) job_logits(p, j, c, ring, L.nxl);
       else job_gemm(p, kind, l, j, c, ring, hrd, hwr);
-      csync();  // all of the job's global stores are issued
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counters + (size_t)pi * 32, 1u);
-      }
+      // every job ends with a CTA barrier behind its last global store: one release-add publishes them
+      if (threadIdx.x == 0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counters + (size_t)pi * 32), "r"(1u) : "memory");
     }
     prof_mark(c, 50 + kind);
   }

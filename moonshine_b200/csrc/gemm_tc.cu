@@ -91,6 +91,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a converged warp (tcgen05.mma wants uniform-register operands: issued under elect.sync inside
+// warp-uniform control flow it is a few instructions; from a divergent `if (tid == X)` the compiler wraps every
+// MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop, ~95 ns per MMA measured on B200).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Splits 4 floats into bf16 hi / lo quads (8 bytes each).
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = (int)uniform_u32((uint32_t)(threadIdx.x >> 5));  // provably warp-uniform
 
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
@@ -219,29 +233,35 @@ __global__ void __launch_bounds__(kThreadsTC, 2) gemm_tc_kernel(const __grid_con
       if (!(dbg & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(&full_bar[s]);
     }
-  } else if (tid == kLoaders) {
-    // ============================ MMA issuer ============================
+  } else {
+    // ============================ MMA issuer (warp 8, one elected lane) ============================
+    const uint32_t tm = uniform_u32(tmem_base);
     for (int kb = 0; kb < nk; kb++) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)((kb / kStages) & 1);
       mbar_wait(&full_bar[s], ph);
+      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytesTC);
+      const uint32_t a_hi = uniform_u32(smem_u32(smem + (size_t)s * kStageBytesTC));
       const uint32_t a_lo = a_hi + kTileBytes;
       const uint32_t w_hi = a_hi + 2 * kTileBytes;
       const uint32_t w_lo = a_hi + 3 * kTileBytes;
+      if (elect_one()) {
 #pragma unroll
-      for (int j = 0; j < TK / 16; j++) {
-        const uint32_t ko = (uint32_t)j * 32u;  // 16 bf16 = 32 bytes along K inside the swizzle atom
-        const uint64_t dah = make_desc_sw64(a_hi + ko), dal = make_desc_sw64(a_lo + ko);
-        const uint64_t dwh = make_desc_sw64(w_hi + ko), dwl = make_desc_sw64(w_lo + ko);
-        umma_bf16(tmem_base, dal, dwh, (kb | j) ? 1u : 0u);  // small terms first
-        umma_bf16(tmem_base, dah, dwl, 1u);
-        umma_bf16(tmem_base, dah, dwh, 1u);
+        for (int j = 0; j < TK / 16; j++) {
+          const uint32_t ko = (uint32_t)j * 32u;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+          const uint64_t dah = make_desc_sw64(a_hi + ko), dal = make_desc_sw64(a_lo + ko);
+          const uint64_t dwh = make_desc_sw64(w_hi + ko), dwl = make_desc_sw64(w_lo + ko);
+          umma_bf16(tm, dal, dwh, (kb | j) ? 1u : 0u);  // small terms first
+          umma_bf16(tm, dah, dwl, 1u);
+          umma_bf16(tm, dah, dwh, 1u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
       }
-      umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+      __syncwarp();
     }
-    umma_commit(&accum_bar);       // accumulator complete
+    if (elect_one()) umma_commit(&accum_bar);  // accumulator complete
+    __syncwarp();
   }
 
   // ============================ epilogue (warps 0-7) ============================

@@ -442,6 +442,7 @@ void Model::build_weights(const WeightFile& wf) {
   {
     const char* e = std::getenv("MOONSHINE_B200_DECODER_GEMV");
     dec_.mma_gemv = !(e && std::string(e) == "simt");
+    if (e && std::string(e) == "mma3") dec_.mma_gemv = 2;  // v3 experiment knob
   }
   for (int l = 0; l < d_.dec_layers; l++) {
     DecLayerWeights& w = dec_.layers[l];

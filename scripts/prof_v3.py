@@ -17,6 +17,8 @@ import sys
 
 NAMES = {0: "start", 1: "S.prologue", 2: "S.qkv", 3: "S.attn", 4: "S.wo", 11: "X.prologue", 12: "X.q", 13: "X.attn",
          22: "OC.x", 23: "FC1.x", 24: "FC2.x", 32: "OC.mma", 33: "FC1.mma", 34: "FC2.mma",
+         60: "s.flags", 61: "s.resolve", 62: "s.ln", 63: "g.sync", 64: "g.issue", 65: "g.acc", 66: "a.scores", 67: "a.softmax",
+         68: "a.pv", 69: "o.acq", 70: "x.scores", 71: "x.softmax", 72: "x.pv", 73: "f.resolve", 74: "g.ring0",
          35: "L.x", 36: "L.issue", 37: "L.acc", 38: "L.epi",
          40: "wait>SELF", 41: "wait>CROSS", 42: "wait>OC", 43: "wait>FC1", 44: "wait>FC2", 45: "wait>FINAL", 46: "wait>LOGITS",
          50: "end.SELF", 51: "end.CROSS", 52: "end.OC", 53: "end.FC1", 54: "end.FC2", 55: "end.FINAL", 56: "end.LOGITS"}

@@ -36,14 +36,31 @@ def test_reference_benchmark_cpp_runs_against_this_library(tmp_path):
         w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
         w.writeframes(pcm16.tobytes())
     r = subprocess.run([exe, "-m", str(model_dir), "-a", "0", "-w", str(wav)], capture_output=True, text=True, timeout=300)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "ref_benchmark_stderr.txt"), "w") as f:
+            f.write(r.stderr)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Transcription took" in r.stderr
-    # the same clip in one shot through this library's own binding (default options on both sides)
+    # the same clip through this library's own binding, fed the way the tool feeds it (default options on both sides)
+    pcm = pcm16.astype(np.float32) / np.float32(32768.0)
     t = api.Transcriber(str(model_dir), api.ModelArch.TINY)
-    tr = t.transcribe_without_streaming(pcm16.astype(np.float32) / np.float32(32768.0))
+    s = t.create_stream()
+    s.start()
+    chunk, every, since = int(0.0214 * 16000), int(0.481 * 16000), 0
+    for i in range(0, len(pcm), chunk):
+        piece = pcm[i:i + chunk]
+        s.add_audio(piece)
+        since += len(piece)
+        if since >= every:
+            since = 0
+            s.update_transcription()
+    s.stop()
+    tr = s.update_transcription()
+    s.close()
     t.close()
     assert len(tr.lines) >= 1
-    for line in tr.lines:
-        assert line.text and line.text in r.stderr, (line.text, r.stderr[-1500:])
+    printed = re.findall(r"\] '(.*)' \(", r.stderr)
+    assert printed == [line.text for line in tr.lines], (printed, [line.text for line in tr.lines])
     m = re.search(r"Average Latency: (\d+)ms", r.stderr)
     assert m is not None

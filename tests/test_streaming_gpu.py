@@ -161,3 +161,30 @@ def test_streaming_arch_through_the_reference_abi():
     s.stop()
     s.close()
     t.close()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "refx_*.npz"))), ids=lambda p: os.path.basename(p)[5:-4])
+def test_streaming_against_reference_graph_modules(path):
+    """CUDA path against fixtures produced by the reference's own export.py graph modules run chunk by chunk with
+    carried state (tests/golden/make_golden_streaming_ref.py) -- no oracle in the loop."""
+    parts = os.path.basename(path)[5:-4].split("_")
+    n, inp, seed, init = int(parts[-1]), parts[-2], int(parts[-3][1:]), parts[-4]
+    arch = "_".join(parts[:-4])
+    g = np.load(path)
+    d = ARCHS[arch]
+    audio = synth_audio(int(inp[5:]), n)
+    toks = g["tokens"]
+    forced = np.zeros((1, len(toks) + 1), np.int32)
+    forced[0, :len(toks)] = toks
+    t = make_transcriber(arch, seed, init)
+    steps = len(toks) - 1
+    mems, logits, _ = t.debug_run([audio], d.dim, d.vocab, forced=forced, logits_steps=steps, max_tokens=300)
+    assert tuple(mems[0].shape) == tuple(g["mem_shape"])
+    assert np.abs(mems[0][::4] - g["mem_sub"]).max() / g["mem_absmax"] < TOL
+    lg = logits[:, 0]
+    assert (np.abs(lg[:, ::64] - g["logits_sub"]).max(1) / g["logits_absmax"]).max() < TOL
+    top = np.take_along_axis(lg, g["top_idx"], 1)
+    assert (np.abs(top - g["top_val"]).max(1) / g["logits_absmax"]).max() < TOL
+    clear = g["margin"] / g["logits_absmax"] > 4 * TOL
+    assert (lg.argmax(1)[clear] == toks[1:][clear]).all()
+    t.close()

@@ -89,3 +89,41 @@ def test_streaming_length_bookkeeping():
     assert streaming_lengths(29500, emitted_before=76, processed_before=29440, is_final=True) == (29440, 92, 92)
     o = StreamingOracle
     assert o.max_tokens_greedy(160000) == 65 and o.max_tokens_greedy(16000 * 60) == 256
+
+
+def refx_cases():
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLD, "refx_*.npz"))):
+        parts = os.path.basename(f)[5:-4].split("_")     # <arch...>_<init>_s<seed>_<input>_<n>
+        n, inp, seed, init = int(parts[-1]), parts[-2], int(parts[-3][1:]), parts[-4]
+        out.append(("_".join(parts[:-4]), init, seed, inp, n, f))
+    return out
+
+
+@pytest.mark.parametrize("arch,init,seed,inp,n,path", refx_cases(), ids=[os.path.basename(c[5])[5:-4] for c in refx_cases()])
+def test_streaming_oracle_matches_reference_graph_modules_run_chunk_by_chunk(arch, init, seed, inp, n, path):
+    """Fixtures from the REFERENCE's own export.py modules (Frontend / Encoder / Adapter / CrossKV / DecoderKV),
+    driven chunk by chunk with carried state over several non-final updates and a final one
+    (tests/golden/make_golden_streaming_ref.py).  The oracle's ONE stateless pass over the analysed audio must give
+    the same memory, logits and ids: "stateless == chunked" pinned to reference code."""
+    g = np.load(path)
+    o = streaming_oracle(arch, seed, init)
+    pcm = synth_audio(int(inp[5:]), n)
+    toks, logits, mem = o.transcribe_segment(pcm, is_final=True, forced=g["tokens"][1:])
+    assert tuple(mem.shape) == tuple(g["mem_shape"]) and mem.shape[0] == int(g["mem_len_after_update"][-1])
+    assert np.abs(mem[::4] - g["mem_sub"]).max() / g["mem_absmax"] < 2e-5
+    assert (np.abs(logits[:, ::64] - g["logits_sub"]).max(1) / g["logits_absmax"]).max() < 2e-5
+    top = np.take_along_axis(logits, g["top_idx"], 1)
+    assert (np.abs(top - g["top_val"]).max(1) / g["logits_absmax"]).max() < 2e-5
+    clear = g["margin"] / g["logits_absmax"] > 1e-4
+    assert (logits.argmax(1)[clear] == g["tokens"][1:][clear]).all()
+    # the memory length after every non-final update follows the same bookkeeping as the product's host code
+    d = ARCHS[arch]
+    processed = emitted = 0
+    for end, want in zip(g["pieces"], g["mem_len_after_update"]):
+        processed, _, emitted = streaming_lengths(int(end), emitted, processed, is_final=(int(end) == n),
+                                                  lookahead=d.total_lookahead)
+        assert emitted == int(want)
+    # one multi-token decoder call (decode_tokens, moonshine-streaming-model.cpp:1136-1190) == the stepped logits
+    k = g["verify_logits_sub"].shape[0]
+    assert (np.abs(logits[:k, ::64] - g["verify_logits_sub"]).max(1) / g["verify_absmax"]).max() < 2e-5
