@@ -297,8 +297,8 @@ __host__ __device__ inline SmemLayout3 smem_layout3(int B, int D, int hd, int Kc
   L.rope = take(128 * 4);
   L.argv = take(kWarpsC * 64 * 4);
   L.argi = take(kWarpsC * 64 * 4);
-  L.sbias = take(256 * 4);            // logit bias: static bonuses of this CTA's vocab chunk,
-  L.rowflag = take(256);              // rows with a per-utterance entry,
+  L.sbias = take(384 * 4);            // logit bias: static bonuses of this CTA's vocab chunk (<= 3 m-tiles),
+  L.rowflag = take(384);              // rows with a per-utterance entry,
   L.ent_key = take(kBiasEntries * 4); // (row << 8 | utterance column) of each entry that falls into the chunk,
   L.ent_val = take(kBiasEntries * 4); // its bonus,
   L.ent_n = take(16);                 // and their count
@@ -1291,7 +1291,7 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
     if (biased) {
       // bonuses that land in this CTA's vocab chunk: the shared ones as a dense slice, the per-utterance ones as
       // (row, utterance column, bonus) entries
-      for (int i = threadIdx.x; i < 256; i += kConsumers) {
+      for (int i = threadIdx.x; i < 384; i += kConsumers) {
         const int v = item * VC + i;
         c.sbias[i] = (p.bias_static != nullptr && i < VC && v < V) ? __ldg(p.bias_static + v) : 0.f;
         c.rowflag[i] = 0;
@@ -1308,7 +1308,7 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
               const int slot = atomicAdd(c.ent_n, 1);
               if (slot >= kBiasEntries) atomicExch(c.err, 2u);  // table overflow: fail the decode, never drop a bonus
               if (slot < kBiasEntries) {
-                c.ent_key[slot] = (loc << 8) | b;
+                c.ent_key[slot] = (loc << 9) | b;
                 c.ent_val[slot] = p.bias_dyn_val[(int64_t)(b0 + b) * cap + k];
                 c.rowflag[loc] = 1;
               }
@@ -1374,58 +1374,64 @@ __device__ void job_logits(const DecoderParams& p, int item, Ctx& c, Ring& ring,
     __syncwarp();
     prof_mark(c, 37);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int mt_w = warp >> 2;                      // warps 0-3: m-tile 0, warps 4-7: m-tile 1
-    const int vrow = mt_w * 128 + (warp & 3) * 32 + lane;
-    const int v = item * VC + vrow;
-    const bool vok = (mt_w < n_mt) && (vrow < VC) && (v < V);
-    for (int cb = 0; cb < nx; cb += 16) {
-      uint32_t r[16];
+    // running best (key, index) of this warp per utterance column; warps 0-3 take m-tiles 0, 2, warps 4-7 m-tile 1
+    for (int b = lane; b < 64; b += 32) { c.argv[warp * 64 + b] = 0.f; c.argi[warp * 64 + b] = 0x7fffffff; }
+    __syncwarp();
+    for (int mt_w = warp >> 2; mt_w < n_mt; mt_w += 2) {
+      const int vrow = mt_w * 128 + (warp & 3) * 32 + lane;
+      const int v = item * VC + vrow;
+      const bool vok = (vrow < VC) && (v < V);
+      for (int cb = 0; cb < nx; cb += 16) {
+        uint32_t r[16];
+        {
+          const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt_w * nx + cb);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (biased && vok) {
+          const float sb = c.sbias[vrow];
 #pragma unroll
-      for (int e = 0; e < 16; e++) r[e] = 0u;
-      if (mt_w < n_mt) {  // warp-uniform
-        const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt_w * nx + cb);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      }
-      if (biased && vok) {
-        const float sb = c.sbias[vrow];
+          for (int e = 0; e < 16; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + sb);
+          if (c.rowflag[vrow]) {  // rare: some utterance's active key-term path continues with this token
+            const int n_ent = min(*c.ent_n, kBiasEntries);
+            for (int s2 = 0; s2 < n_ent; s2++) {
+              const int key = c.ent_key[s2];
+              const int col = (key & 511) - cb;
+              if ((key >> 9) == vrow && col >= 0 && col < 16) {
+                const float add = c.ent_val[s2];
 #pragma unroll
-        for (int e = 0; e < 16; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + sb);
-        if (c.rowflag[vrow]) {  // rare: some utterance's active key-term path continues with this token
-          const int n_ent = min(*c.ent_n, kBiasEntries);
-          for (int s2 = 0; s2 < n_ent; s2++) {
-            const int key = c.ent_key[s2];
-            const int col = (key & 255) - cb;
-            if ((key >> 8) == vrow && col >= 0 && col < 16) {
-              const float add = c.ent_val[s2];
-#pragma unroll
-              for (int e = 0; e < 16; e++)
-                if (e == col) r[e] = __float_as_uint(__uint_as_float(r[e]) + add);
+                for (int e = 0; e < 16; e++)
+                  if (e == col) r[e] = __float_as_uint(__uint_as_float(r[e]) + add);
+              }
             }
           }
         }
-      }
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        const int b = cb + e;
-        const float val = __uint_as_float(r[e]);
-        if (vok && p.logits_out && b < nb) p.logits_out[(int64_t)(b0 + b) * V + v] = val;
-        // order-preserving float -> uint key (NaN and masked rows -> 0, never win); one redux gives the warp max,
-        // the lowest lane holding it is the first (smallest) vocab index
-        uint32_t key = r[e];
-        key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
-        if (!vok || val != val) key = 0u;
-        const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
-        const uint32_t who = __ballot_sync(0xffffffffu, key == mx);
-        if (lane == 0) {
-          c.argv[warp * 64 + b] = __uint_as_float(mx);
-          c.argi[warp * 64 + b] = mx ? item * VC + mt_w * 128 + (warp & 3) * 32 + (__ffs(who) - 1) : 0x7fffffff;
+        for (int e = 0; e < 16; e++) {
+          const int b = cb + e;
+          const float val = __uint_as_float(r[e]);
+          if (vok && p.logits_out && b < nb) p.logits_out[(int64_t)(b0 + b) * V + v] = val;
+          // order-preserving float -> uint key (NaN and masked rows -> 0, never win); one redux gives the warp max,
+          // the lowest lane holding it is the first (smallest) vocab index
+          uint32_t key = r[e];
+          key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+          if (!vok || val != val) key = 0u;
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+          const uint32_t who = __ballot_sync(0xffffffffu, key == mx);
+          if (lane == 0 && mx != 0u) {
+            const int idx = item * VC + mt_w * 128 + (warp & 3) * 32 + (__ffs(who) - 1);
+            const uint32_t cur_key = __float_as_uint(c.argv[warp * 64 + b]);
+            if (mx > cur_key || (mx == cur_key && idx < c.argi[warp * 64 + b])) {
+              c.argv[warp * 64 + b] = __uint_as_float(mx);
+              c.argi[warp * 64 + b] = idx;
+            }
+          }
         }
       }
     }

@@ -147,6 +147,12 @@ struct DecLayerWeights {
   const unsigned char* w1iF;   // one block N = 2*I, K = D         rows interleaved: 2j = value j, 2j+1 = gate j
   const float* b1i;            // [2*I] fc1 bias in the same interleaved order
   const unsigned char* w2kF;   // [ffn_ksplit] blocks N = D, K = I / ffn_ksplit  (k-slices of fc2)
+  // v4 kernel (cluster-resident layers): fp32 k-major slices per cluster rank r (CS ranks)
+  const float* c4_wo;          // [CS][D][dsp]      output features r*D/CS .. of the self-attention output projection
+  const float* c4_woc;         // [CS][D][dsp]      the same for the cross-attention output projection
+  const float* c4_w1;          // [CS][D][2*I/CS]   fc1 columns of the rank's FFN slice, (value j, gate j) interleaved, x ln3 gamma
+  const float* c4_b1;          // [CS][2*I/CS]
+  const float* c4_w2;          // [CS][I/CS][D]     fc2 rows (inputs) of the rank's FFN slice
 };
 // bytes of one plane-packed [N][K] block
 inline size_t decoder_plane_bytes(int N, int K) {
@@ -208,6 +214,7 @@ struct DecoderParams {
   unsigned int* sync3;    // [kSync3Words] epoch, error flag, one completion counter per phase (own 128-byte line)
   // sparse logit bonuses added in the logits epilogue before the fused argmax (key-term biasing,
   // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
+  int c4_cs, c4_nc, c4_u;     // v4: cluster size, clusters, utterances per cluster
   const float* bias_static;   // [V] bonus shared by every utterance and step (the trie root's children)
   const int* bias_dyn_n;      // [B] per-utterance entries of this step
   const int* bias_dyn_ids;    // [B][bias_dyn_cap] token ids
@@ -220,6 +227,12 @@ size_t decoder_step3_smem_bytes(const DecoderParams& p);
 // fills nb_self / nb_cross / nx / job_first / job_ncta for batch size p.B on a grid of `grid` CTAs
 void decoder_step3_plan(DecoderParams& p, int grid);
 bool decoder_step3_supported(const DecoderParams& p);
+// v4: cluster-resident layers for small batches (<= 8 utterances per cluster of 16 or 8 CTAs)
+int decoder_step4_cluster_size(int device, int heads, size_t smem_hint, int* clusters);  // 16, 8 or 0 (none)
+bool decoder_step4_supported(const DecoderParams& p);
+void decoder_step4_plan(DecoderParams& p);
+size_t decoder_step4_smem_bytes(const DecoderParams& p);
+void launch_decoder_step4(const DecoderParams& p, cudaStream_t stream);
 // out[b] = id emitted by the step that was just launched (p.step), resolved from its argmax candidates with the
 // reference's lowest-index tie rule; the next launch's prologue resolves the same value on its own.
 void launch_decoder_resolve(const DecoderParams& p, int* out, cudaStream_t stream);

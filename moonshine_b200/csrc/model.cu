@@ -93,18 +93,31 @@ Model::Model(const Dims& dims, const WeightFile& weights, int device) : d_(dims)
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   for (auto& e : ev_) CUDA_CHECK(cudaEventCreate(&e));
   if (d_.dec_layers > kMaxDecLayers) throw std::runtime_error("too many decoder layers");
-  {
-    int per = (d_.vocab + sm_count_ - 1) / sm_count_;
-    per = round_up(std::max(per, 32), 32);
-    if (per > 256) per = 256;
-    vchunk_ = per;
-    n_vchunk_ = (d_.vocab + per - 1) / per;
-  }
   CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
   {
     const char* e = std::getenv("MOONSHINE_B200_DECODER");
     decoder_v2_ = !(e && std::string(e) == "v1");
     decoder_v3_ = !(e && (std::string(e) == "v1" || std::string(e) == "v2"));
+  }
+  {
+    // v4 (cluster-resident layers) serves small batches of small models: every cluster streams all layer weights,
+    // so they have to stay L2-resident next to the streamed cross K/V
+    const char* e = std::getenv("MOONSHINE_B200_DECODER");
+    const bool want_v4 = decoder_v3_ && !(e && std::string(e) == "v3");
+    const double layer_mb = (double)d_.dec_layers * (4.0 * d_.dim * d_.dim + 3.0 * d_.dim * d_.ffn) * 4.0 / 1e6;
+    c4_cs_ = 0;
+    if (want_v4 && layer_mb <= 48.0 && d_.dim % 32 == 0)
+      c4_cs_ = decoder_step4_cluster_size(device_, d_.heads, (size_t)smem_optin_, &c4_nc_);
+    if (c4_cs_ > 0 && (d_.dim % c4_cs_ || d_.ffn % c4_cs_ || ((2 * d_.ffn / c4_cs_) % 4) || c4_cs_ % d_.heads)) c4_cs_ = 0;
+  }
+  {
+    // vocab chunks of the logits phase: one per CTA of the kernel that will run it (128 with clusters, else one per SM)
+    const int ctas = c4_cs_ > 0 ? c4_cs_ * c4_nc_ : sm_count_;
+    int per = (d_.vocab + ctas - 1) / ctas;
+    per = round_up(std::max(per, 32), 32);
+    if (per > 384) per = 384;   // <= 3 m-tiles of 128 vocab rows per chunk
+    vchunk_ = per;
+    n_vchunk_ = (d_.vocab + per - 1) / per;
   }
   build_weights(weights);
   barrier_.reserve(2);
@@ -291,7 +304,8 @@ void Model::build_weights(const WeightFile& wf) {
   size_t o_decln = o_ones;
   size_t o_wk_all = bb.add((size_t)d_.dec_layers * D * D);
   size_t o_wv_all = bb.add((size_t)d_.dec_layers * D * D);
-  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2, wqkvP, woP, wqcP, wocP, w1P, w2P, wocF, w1iF, b1i, w2kF; };
+  struct DecOff { size_t ln1, wqkv, wo, ln2, wqc, woc, ln3, w1, b1, w2, b2, wqkvP, woP, wqcP, wocP, w1P, w2P, wocF, w1iF, b1i, w2kF,
+                  c4_wo, c4_woc, c4_w1, c4_b1, c4_w2; };
   // fc2 k-slices of the v3 kernel: the smallest split whose slice is no wider than max(D, 256) inputs
   ffn_ksplit_ = 1;
   for (int k = 1; k <= 16; k++)
@@ -408,6 +422,37 @@ void Model::build_weights(const WeightFile& wf) {
         if (ks == 0) dof[l].w2kF = a;
       }
     }
+    // v4 kernel: fp32 k-major slices per cluster rank
+    if (c4_cs_ > 0) {
+      const int CS = c4_cs_, ds = D / CS, dsp = (ds + 3) & ~3, is = I / CS;
+      dof[l].c4_wo = bb.add((size_t)CS * D * dsp);
+      dof[l].c4_woc = bb.add((size_t)CS * D * dsp);
+      dof[l].c4_w1 = bb.add((size_t)CS * D * 2 * is);
+      dof[l].c4_b1 = bb.add((size_t)CS * 2 * is);
+      dof[l].c4_w2 = bb.add((size_t)CS * is * D);
+      for (int r = 0; r < CS; r++) {
+        float* wo_s = &bb.data[dof[l].c4_wo + (size_t)r * D * dsp];
+        float* woc_s = &bb.data[dof[l].c4_woc + (size_t)r * D * dsp];
+        for (int kk = 0; kk < D; kk++)
+          for (int j = 0; j < ds; j++) {
+            wo_s[(size_t)kk * dsp + j] = o[(size_t)(r * ds + j) * D + kk];
+            woc_s[(size_t)kk * dsp + j] = oc[(size_t)(r * ds + j) * D + kk];
+          }
+        float* w1_s = &bb.data[dof[l].c4_w1 + (size_t)r * D * 2 * is];
+        float* b1_s = &bb.data[dof[l].c4_b1 + (size_t)r * 2 * is];
+        float* w2_s = &bb.data[dof[l].c4_w2 + (size_t)r * is * D];
+        for (int j = 0; j < is; j++) {
+          const int f = r * is + j;                 // FFN feature of this rank
+          b1_s[2 * j] = f1b[f];                     // value ("up")
+          b1_s[2 * j + 1] = f1b[I + f];             // gate
+          for (int kk = 0; kk < D; kk++) {
+            w1_s[(size_t)kk * 2 * is + 2 * j] = f1[(size_t)f * D + kk] * g3[kk];
+            w1_s[(size_t)kk * 2 * is + 2 * j + 1] = f1[(size_t)(I + f) * D + kk] * g3[kk];
+          }
+          for (int n = 0; n < D; n++) w2_s[(size_t)j * D + n] = f2[(size_t)n * I + f];
+        }
+      }
+    }
     std::memcpy(&bb.data[o_wk_all + (size_t)l * D * D], kc, sizeof(float) * D * D);
     std::memcpy(&bb.data[o_wv_all + (size_t)l * D * D], vc, sizeof(float) * D * D);
   }
@@ -437,6 +482,7 @@ void Model::build_weights(const WeightFile& wf) {
   std::memset(&dec_, 0, sizeof(dec_));
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
+  dec_.c4_cs = c4_cs_; dec_.c4_nc = c4_nc_;
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   {
@@ -453,6 +499,10 @@ void Model::build_weights(const WeightFile& wf) {
     w.wocP = bytes + dof[l].wocP * 4; w.w1P = bytes + dof[l].w1P * 4; w.w2P = bytes + dof[l].w2P * 4;
     w.wocF = decoder_v2_ ? bytes + dof[l].wocF * 4 : nullptr; w.w1iF = bytes + dof[l].w1iF * 4;
     w.b1i = base + dof[l].b1i; w.w2kF = bytes + dof[l].w2kF * 4;
+    if (c4_cs_ > 0) {
+      w.c4_wo = base + dof[l].c4_wo; w.c4_woc = base + dof[l].c4_woc; w.c4_w1 = base + dof[l].c4_w1;
+      w.c4_b1 = base + dof[l].c4_b1; w.c4_w2 = base + dof[l].c4_w2;
+    }
     w.ln3 = base + dof[l].ln3; w.w1 = base + dof[l].w1; w.b1 = base + dof[l].b1;
     w.w2 = base + dof[l].w2; w.b2 = base + dof[l].b2;
   }
@@ -1001,9 +1051,14 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   // positions, so clips longer than ~39 s (Tpad > 1024) take the v1 kernel.
   const bool use_v2 = decoder_v2_ && Tpad <= 1024 && hd <= 64 && d_.rot_dim <= 128 && D % 32 == 0;
   const bool use_v3 = use_v2 && decoder_v3_ && decoder_step3_supported(p);
-  if (use_v3) decoder_step3_plan(p, grid);
+  const bool use_v4 = use_v3 && c4_cs_ > 0 && decoder_step4_supported(p);
+  if (use_v4) decoder_step4_plan(p);
+  else if (use_v3) decoder_step3_plan(p, grid);
+  if (std::getenv("MOONSHINE_B200_VERBOSE"))
+    MSB_LOGF("decoder kernel: %s (B=%d, cluster size %d)", use_v4 ? "v4" : use_v3 ? "v3" : use_v2 ? "v2" : "v1", B, c4_cs_);
   auto launch_step = [&]() {
-    if (use_v3) launch_decoder_step3(p, grid, stream_);
+    if (use_v4) launch_decoder_step4(p, stream_);
+    else if (use_v3) launch_decoder_step3(p, grid, stream_);
     else if (use_v2) launch_decoder_step2(p, grid, stream_);
     else launch_decoder_step(p, grid, stream_);
   };

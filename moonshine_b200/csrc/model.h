@@ -140,6 +140,8 @@ class Model {
   bool decoder_v2_ = true;
   bool decoder_v3_ = true;
   int ffn_ksplit_ = 1;
+  int c4_cs_ = 0;   // cluster size of the v4 decoder kernel (0: not used)
+  int c4_nc_ = 0;   // co-resident clusters of that size
 
   // rope tables (grow-only)
   DeviceBuffer<float> rope_cos_, rope_sin_;

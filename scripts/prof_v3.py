@@ -24,12 +24,21 @@ NAMES = {0: "start", 1: "S.prologue", 2: "S.qkv", 3: "S.attn", 4: "S.wo", 11: "X
          50: "end.SELF", 51: "end.CROSS", 52: "end.OC", 53: "end.FC1", 54: "end.FC2", 55: "end.FINAL", 56: "end.LOGITS"}
 
 
-def main(path):
+NAMES4 = {0: "start", 1: "embed", 10: "qkv", 11: "o", 12: "qc", 13: "oc", 14: "fc1", 15: "fc2", 20: "selfattn+CB", 21: "h+CB", 22: "cross+CB",
+          23: "h+CB'", 24: "silu", 25: "CB", 30: "final+handoff", 31: "logits", 40: "rope", 41: "a.scores", 43: "a.pv", 44: "a.bcast",
+          45: "x.scores", 46: "x.softmax", 47: "x.pv", 48: "CB(part)", 49: "reduce", 50: "g.acq", 51: "g.rows", 52: "g.sync"}
+
+
+def main(path, v4=False):
+    global NAMES
+    if v4:
+        NAMES = NAMES4
+    scale = 1.0 / 1.965 if v4 else 1.0   # v4 stamps are raw SM cycles
     for line in open(path):
         m = re.match(r"PROF cta (\d+):(.*)", line)
         if not m:
             continue
-        stamps = [(int(a), int(b)) for a, b in re.findall(r"(\d+):(\d+)", m.group(2))]
+        stamps = [(int(a), int(b) * scale) for a, b in re.findall(r"(\d+):(\d+)", m.group(2))]
         if len(stamps) < 2:
             continue
         tot = collections.OrderedDict()
@@ -43,4 +52,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], v4="--v4" in sys.argv)
