@@ -106,12 +106,17 @@ def hf_arm(model, audios_serial, audios_batch, threads):
     torch.set_num_threads(threads)
     weights = synth_weights(model, 0, "hf")
     m = hf.hf_model(ARCHS[model], weights)
-    hf.time_serial(m, audios_serial[:1], threads)  # warm-up (allocator, thread pool)
-    s_dt, s_tok = hf.time_serial(m, audios_serial, threads)
-    b_dt, b_tok = hf.time_batched(m, audios_batch, threads)
+    # the thread count that is fastest on THIS host for each shape (all cores is not: see hf.pick_threads)
+    t_serial, seen_s = hf.pick_threads(m, audios_serial, threads, 1)
+    s_dt, s_tok = hf.time_serial(m, audios_serial, t_serial)
+    t_batch, seen_b = hf.pick_threads(m, audios_batch, threads, len(audios_batch))
+    b_dt, b_tok = hf.time_batched(m, audios_batch, t_batch)
     return {"serial_s_per_utt": s_dt / len(audios_serial), "serial_utt_s": len(audios_serial) / s_dt,
             "serial_n": len(audios_serial), "batched_utt_s": len(audios_batch) / b_dt, "batched_n": len(audios_batch),
-            "batched_s": b_dt, "tokens_serial": s_tok, "tokens_batched": b_tok, "model": m}
+            "batched_s": b_dt, "tokens_serial": s_tok, "tokens_batched": b_tok, "model": m,
+            "threads_serial": t_serial, "threads_batched": t_batch,
+            "threads_tried": {"serial": {str(k): round(v, 3) for k, v in seen_s.items()},
+                              "batched": {str(k): round(v, 3) for k, v in seen_b.items()}}}
 
 
 def numpy_port_utt_s(model, audio, threads):
@@ -145,14 +150,19 @@ def run_reference(args):
         torch.set_num_threads(threads)
         m = hf.hf_model(ARCHS[model], synth_weights(model, 0, "hf"))
         kind_note = "Hugging Face transformers MoonshineForConditionalGeneration, fp32, eager attention, KV cache"
-        for _ in range(max(1, min(args.warmup, 2))):
+        cores = threads
+        threads, seen_b = hf.pick_threads(m, audios, cores, len(audios))   # warm-up included
+        for _ in range(max(0, min(args.warmup, 2) - 1)):
             hf.time_batched(m, audios[:4], threads)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             hf.time_batched(m, audios, threads)
         dt = time.perf_counter() - t0
-        serial_dt, _ = hf.time_serial(m, audios[:3], threads)
-        serial = {"serial_batch1_s_per_utt": serial_dt / 3, "serial_batch1_utt_s": 3 / serial_dt}
+        t_serial, seen_s = hf.pick_threads(m, audios, cores, 1)
+        serial_dt, _ = hf.time_serial(m, audios[:3], t_serial)
+        serial = {"serial_batch1_s_per_utt": serial_dt / 3, "serial_batch1_utt_s": 3 / serial_dt, "serial_threads": t_serial,
+                  "threads_tried_s_per_short_sample": {"batched": {str(k): round(v, 3) for k, v in seen_b.items()},
+                                                       "serial": {str(k): round(v, 3) for k, v in seen_s.items()}}}
     except Exception as e:  # transformers missing on the box: fall back to the numpy port, say so
         kind_note = f"numpy oracle port (HF arm unavailable: {type(e).__name__})"
         B = 2
@@ -256,6 +266,7 @@ def measure_config(api, torch, dist, model, B, steps, warmup, rank, world, local
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
     dev_total_ms, e2e_total = [float(x) for x in t.tolist()]
     steps_run = int(tm["decode_steps"])
+    dec_kernel = "decoder_step%d_kernel" % int(tm.get("decoder_version", 3) or 3)
     tr.close()
     del dev, flush
     torch.cuda.empty_cache()
@@ -280,7 +291,7 @@ def measure_config(api, torch, dist, model, B, steps, warmup, rank, world, local
         "rtf": (dev_total_ms / 1000.0) / (utts * 10.0),
         "stage_ms": {"frontend": float(np.mean(fe_ms)), "encoder": float(np.mean(enc_ms)), "cross_kv": float(np.mean(xkv_ms)),
                      "decode": float(np.mean(dec_ms)), "decode_launch_us": 1000.0 * launch_ms, "decode_steps": steps_run},
-        "roofline": {"kernel": "decoder_step3_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": dec_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": measured_traffic().get(key), "bytes_per_launch": bytes_per_launch,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
         "gpu_launches": launches_per_step * steps,
@@ -377,9 +388,11 @@ def main():
                 r = hf_arm(model, audios[:3], audios[:min(B, 16)], threads)
                 n = r["serial_n"]
                 line["cpu_baseline"] = {
-                    "value": r["batched_utt_s"], "unit": "utt/s", "cores": threads, "kind": "port",
-                    "sample": f"first {r['batched_n']} utterances of the batch as ONE batch ({r['batched_s']:.1f} s) and first {n} "
-                              f"one at a time, Hugging Face float implementation (fp32, torch, {threads} threads of {os.cpu_count()} host cores)",
+                    "value": r["batched_utt_s"], "unit": "utt/s", "cores": r["threads_batched"], "kind": "port",
+                    "sample": f"first {r['batched_n']} utterances of the batch as ONE batch ({r['batched_s']:.1f} s, {r['threads_batched']} threads) and "
+                              f"first {n} one at a time ({r['threads_serial']} threads), Hugging Face float implementation (fp32, torch; thread "
+                              f"counts are the fastest of those tried on this {os.cpu_count()}-core host)",
+                    "threads_tried_s_per_short_sample": r["threads_tried"],
                     "serial_batch1_utt_s": r["serial_utt_s"], "serial_batch1_s_per_utt": r["serial_s_per_utt"],
                     "tokens_match_gpu": bool(all(r["tokens_serial"][i] == toks[i] for i in range(n))),
                 }

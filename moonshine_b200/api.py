@@ -391,7 +391,7 @@ class Transcriber:
         out = (ctypes.c_double * 8)()
         _check(self._lib.moonshine_b200_last_timings(self._handle, out), "last_timings")
         keys = ["frontend_ms", "encoder_ms", "cross_kv_ms", "decode_ms", "decode_steps", "kernel_launches",
-                "weight_bytes"]
+                "weight_bytes", "decoder_version"]
         return {k: out[i] for i, k in enumerate(keys)}
 
     def debug_stream_partial(self, enabled: bool):

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <set>
 
+#include <cuda_runtime.h>
 #include "../../include/moonshine_b200.h"
 #include "transcriber.h"
 #include "word_alignment.h"
@@ -82,6 +83,24 @@ void parse_options(const moonshine_option_t* options, uint64_t count, Transcribe
     else if (name == "context") out.context = value;
     else if (name == "context_max_terms") out.context_max_terms = int_from_string(value);
     else if (name == "device") out.device = int_from_string(value);  // additive
+    else if (name == "devices") {                                      // additive: "0,1,2,3" or "all"
+      out.devices.clear();
+      if (value == "all") {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+        for (int i = 0; i < n; i++) out.devices.push_back(i);
+      } else {
+        size_t start = 0;
+        while (start <= value.size()) {
+          const size_t end = value.find(',', start);
+          const std::string tok = value.substr(start, end == std::string::npos ? std::string::npos : end - start);
+          if (!tok.empty()) out.devices.push_back(int_from_string(tok));
+          if (end == std::string::npos) break;
+          start = end + 1;
+        }
+      }
+      if (out.devices.empty()) throw std::runtime_error("option 'devices' names no device");
+    }
     // accepted for compatibility, no effect on this runtime (ORT / CPU-side features)
     else if (name == "save_input_wav_path" || name == "log_ort_run" ||
              name == "diarization_cluster_cadence" ||
@@ -415,7 +434,7 @@ int32_t moonshine_b200_last_timings(int32_t transcriber_handle, double* out8) {
   const StageTimes& s = t->model()->last_times();
   out8[0] = s.frontend_ms; out8[1] = s.encoder_ms; out8[2] = s.cross_kv_ms; out8[3] = s.decode_ms;
   out8[4] = s.decode_steps; out8[5] = s.kernel_launches; out8[6] = (double)t->model()->weight_bytes();
-  out8[7] = 0;
+  out8[7] = s.decoder_version;
   return MOONSHINE_ERROR_NONE;
 }
 

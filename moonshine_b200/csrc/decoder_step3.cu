@@ -132,6 +132,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {  // bytes: multiple of 16
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// this CTA's 1/G share of a block, in 16 KB pieces (`piece` runs on across the blocks of one call site)
+__device__ __forceinline__ void l2_prefetch_share(const void* src, size_t bytes, int& piece) {
+  const int G = (int)gridDim.x, me = (int)blockIdx.x;
+  for (size_t o = 0; o < bytes; o += 16384, piece++)
+    if (piece % G == me) l2_prefetch(reinterpret_cast<const char*>(src) + o, (uint32_t)min((size_t)16384, bytes - o));
+}
+
 // ---- tcgen05 helpers ----
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -210,11 +227,12 @@ struct Ring {
     advance();
   }
   // producers (one lane per producer warp; every producer walks the whole sequence and issues its share)
-  __device__ __forceinline__ void produce(const void* src, uint32_t bytes) {
+  __device__ __forceinline__ void produce(const void* src, uint32_t bytes, uint64_t policy = 0) {
     if (turn == 0) {
       mbar_wait(&empty[st], par ^ 1u, err);
       mbar_expect_tx(&full[st], bytes);
-      bulk_g2s(data + (size_t)st * kStageBytes, src, bytes, &full[st]);
+      if (policy) bulk_g2s_hint(data + (size_t)st * kStageBytes, src, bytes, &full[st], policy);
+      else bulk_g2s(data + (size_t)st * kStageBytes, src, bytes, &full[st]);
       turn = kProducers;
     }
     turn--;
@@ -267,11 +285,11 @@ __device__ __forceinline__ void produce_block_f32(Ring& ring, const float* Wt, i
     ring.produce(Wt + (size_t)k0 * N, (uint32_t)rows * N * 4);
   }
 }
-__device__ __forceinline__ void produce_block_f16(Ring& ring, const __half* M, int rows, int cols) {
+__device__ __forceinline__ void produce_block_f16(Ring& ring, const __half* M, int rows, int cols, uint64_t policy = 0) {
   const int rpc = rows_per_chunk_f16(rows, cols);
   for (int r0 = 0; r0 < rows; r0 += rpc) {
     const int n = min(rpc, rows - r0);
-    ring.produce(M + (size_t)r0 * cols, (uint32_t)n * cols * 2);
+    ring.produce(M + (size_t)r0 * cols, (uint32_t)n * cols * 2, policy);
   }
 }
 
@@ -950,12 +968,30 @@ __device__ __forceinline__ void produce_cross(const DecoderParams& p, int l, int
   const int h = job % H, b0 = (job / H) * nb;
   if (!tile_active(p, active, nb, b0)) return;
   const DecLayerWeights& w = p.layers[l];
+  // The ring alone keeps ~4 x 32 KB in flight per SM: at HBM latency under load that is ~25 GB/s per SM, a third of
+  // what 128 streaming CTAs need to fill HBM.  A sliding window of L2 prefetches (kCrossWindow utterances ahead of the
+  // ring) multiplies the bytes in flight; the ring copies then hit L2 and mark the lines evict-first on the way out,
+  // so the 191 MB a layer streams does not push the next phase's (prefetched) weights out of L2.
+  constexpr int kCrossWindow = 3;
+  const uint32_t kv_bytes = (uint32_t)(hd * p.Tpad * 2);
+  const bool window = (p.pf_mask & 16) != 0 && ring.turn == 0;  // one of the producer lanes (fixed for the whole job)
+  uint64_t pol = 0;
+  if (p.pf_mask & 32) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  auto ask = [&](int b) {
+    if (b >= nb || b0 + b >= p.B || !active[b0 + b]) return;
+    const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+    l2_prefetch(p.kc + bh * hd * p.Tpad, kv_bytes);
+    l2_prefetch(p.vc + bh * p.Tpad * hd, kv_bytes);
+  };
+  if (window)
+    for (int b = 0; b < kCrossWindow; b++) ask(b);
   produce_block_planes(ring, w.wqcP + (size_t)h * plane_block_bytes(hd, D), hd, D);
   for (int b = 0; b < nb; b++) {
+    if (window) ask(b + kCrossWindow);
     if (b0 + b >= p.B || !active[b0 + b]) continue;
     const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
-    produce_block_f16(ring, p.kc + bh * hd * p.Tpad, hd, p.Tpad);   // K^T [hd][Tpad]
-    produce_block_f16(ring, p.vc + bh * p.Tpad * hd, p.Tpad, hd);   // V   [Tpad][hd]
+    produce_block_f16(ring, p.kc + bh * hd * p.Tpad, hd, p.Tpad, pol);   // K^T [hd][Tpad]
+    produce_block_f16(ring, p.vc + bh * p.Tpad * hd, p.Tpad, hd, pol);   // V   [Tpad][hd]
   }
 }
 
@@ -1528,6 +1564,23 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
         const int l = pi / kPhasesPerLayer;
         const int kind = l < p.L ? pi - l * kPhasesPerLayer : PH_FINAL + (pi - p.L * kPhasesPerLayer);
         if (kind == PH_FINAL) continue;  // no ring traffic
+        // Next phase's weight blocks -> L2, this CTA's 1/G share (the producer runs a ring ahead of the consumers, so
+        // this is issued roughly one phase before the blocks are asked for by every CTA that shares them at once).
+        if ((p.pf_mask & 8) && (threadIdx.x - kConsumers) < 32) {
+          int piece = 0;
+          const DecLayerWeights& w = p.layers[l < p.L ? l : 0];
+          if (kind == PH_LOGITS) {  // the next launch's first blocks (the weights do not change between steps)
+            l2_prefetch_share(w.wqkvP, (size_t)p.H * plane_block_bytes(3 * p.hd, p.D), piece);
+            l2_prefetch_share(w.wo, (size_t)p.D * p.D * 4, piece);
+          } else if (kind == PH_SELF) l2_prefetch_share(w.wqcP, (size_t)p.H * plane_block_bytes(p.hd, p.D), piece);
+          else if (kind == PH_CROSS) l2_prefetch_share(w.wocF, plane_block_bytes(p.D, p.D), piece);
+          else if (kind == PH_OC) l2_prefetch_share(w.w1iF, plane_block_bytes(2 * p.I, p.D), piece);
+          else if (kind == PH_FC1) l2_prefetch_share(w.w2kF, (size_t)p.ffn_ksplit * plane_block_bytes(p.D, p.I / p.ffn_ksplit), piece);
+          else if (kind == PH_FC2 && l + 1 < p.L) {
+            l2_prefetch_share(p.layers[l + 1].wqkvP, (size_t)p.H * plane_block_bytes(3 * p.hd, p.D), piece);
+            l2_prefetch_share(p.layers[l + 1].wo, (size_t)p.D * p.D * 4, piece);
+          }
+        }
         const int njobs = phase_jobs(p, kind);
         int j0, stride;
         my_jobs(p, kind, njobs, j0, stride);

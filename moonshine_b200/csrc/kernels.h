@@ -215,6 +215,7 @@ struct DecoderParams {
   // sparse logit bonuses added in the logits epilogue before the fused argmax (key-term biasing,
   // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
   int c4_cs, c4_nc, c4_u;     // v4: cluster size, clusters, utterances per cluster
+  int pf_mask;                // L2 prefetch pipelines: v4 bit 0 weights, 1 cross K/V, 2 vocabulary slab; v3 bit 3 next-phase weights, 4 cross K/V window, 5 evict-first K/V
   const float* bias_static;   // [V] bonus shared by every utterance and step (the trie root's children)
   const int* bias_dyn_n;      // [B] per-utterance entries of this step
   const int* bias_dyn_ids;    // [B][bias_dyn_cap] token ids

@@ -126,6 +126,73 @@ Model::Model(const Dims& dims, const WeightFile& weights, int device) : d_(dims)
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
+Model::Model(const Model& src, int device) : d_(src.d_), device_(device) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10) throw std::runtime_error(format("moonshine-b200 requires an sm_100a GPU, device %d is sm_%d%d", device_, prop.major, prop.minor));
+  sm_count_ = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (auto& e : ev_) CUDA_CHECK(cudaEventCreate(&e));
+  CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+  decoder_v2_ = src.decoder_v2_; decoder_v3_ = src.decoder_v3_;
+  ffn_chunk_ = src.ffn_chunk_; ffn_ksplit_ = src.ffn_ksplit_; vchunk_ = src.vchunk_; n_vchunk_ = src.n_vchunk_;
+  s_k_ = src.s_k_;
+  c4_cs_ = src.c4_cs_; c4_nc_ = src.c4_nc_;
+  if (c4_cs_ > 0) {  // the weight layouts follow the source's cluster shape: this device must host it too
+    int nc = 0;
+    const int cs = decoder_step4_cluster_size(device_, d_.heads, (size_t)smem_optin_, &nc);
+    if (cs != c4_cs_ || nc < c4_nc_) throw std::runtime_error("replica device cannot host the source device's cluster shape");
+  }
+  if (sm_count_ != src.sm_count_ && c4_cs_ == 0) throw std::runtime_error("replica device has a different SM count");
+  // the one weight transfer: device to device
+  wblob_.reserve(src.wblob_.count);
+  int can = 0;
+  if (device_ != src.device_ && cudaDeviceCanAccessPeer(&can, device_, src.device_) == cudaSuccess && can) {
+    cudaDeviceEnablePeerAccess(src.device_, 0);  // already-enabled is fine
+    cudaGetLastError();
+  }
+  CUDA_CHECK(cudaMemcpyPeerAsync(wblob_.ptr, device_, src.wblob_.ptr, src.device_, src.wblob_.bytes(), stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  // every weight pointer is an offset into the blob: rebase
+  const char* ob = reinterpret_cast<const char*>(src.wblob_.ptr);
+  const char* nb = reinterpret_cast<const char*>(wblob_.ptr);
+  auto rb = [&](const float* q) -> const float* {
+    return q == nullptr ? nullptr : reinterpret_cast<const float*>(nb + (reinterpret_cast<const char*>(q) - ob));
+  };
+  auto rbb = [&](const unsigned char* q) -> const unsigned char* {
+    return q == nullptr ? nullptr : reinterpret_cast<const unsigned char*>(nb + (reinterpret_cast<const char*>(q) - ob));
+  };
+  w1t_ = rb(src.w1t_); gn_w_ = rb(src.gn_w_); gn_b_ = rb(src.gn_b_);
+  conv2_w_ = rb(src.conv2_w_); conv2_b_ = rb(src.conv2_b_); conv3_w_ = rb(src.conv3_w_); conv3_b_ = rb(src.conv3_b_);
+  enc_final_ln_ = rb(src.enc_final_ln_);
+  s_lin_w_ = rb(src.s_lin_w_); s_c1_w_ = rb(src.s_c1_w_); s_c1_b_ = rb(src.s_c1_b_); s_c2_w_ = rb(src.s_c2_w_); s_c2_b_ = rb(src.s_c2_b_);
+  pos_emb_ = rb(src.pos_emb_); proj_w_ = rb(src.proj_w_);
+  wk_all_ = rb(src.wk_all_); wv_all_ = rb(src.wv_all_);
+  enc_ = src.enc_;
+  for (EncLayer& e : enc_) {
+    e.ln1 = rb(e.ln1); e.wqk = rb(e.wqk); e.wv = rb(e.wv); e.wo = rb(e.wo); e.ln2 = rb(e.ln2);
+    e.w1 = rb(e.w1); e.b1 = rb(e.b1); e.w2 = rb(e.w2); e.b2 = rb(e.b2);
+  }
+  dec_ = src.dec_;
+  dec_.embed = rb(src.dec_.embed); dec_.embT = rb(src.dec_.embT); dec_.final_ln = rb(src.dec_.final_ln);
+  dec_.embP = rbb(reinterpret_cast<const unsigned char*>(src.dec_.embP));
+  dec_.smem_limit = smem_optin_;
+  for (int l = 0; l < d_.dec_layers; l++) {
+    DecLayerWeights& w = dec_.layers[l];
+    const DecLayerWeights& o = src.dec_.layers[l];
+    w.ln1 = rb(o.ln1); w.wqkv = rb(o.wqkv); w.wo = rb(o.wo); w.ln2 = rb(o.ln2); w.wqc = rb(o.wqc); w.woc = rb(o.woc);
+    w.ln3 = rb(o.ln3); w.w1 = rb(o.w1); w.b1 = rb(o.b1); w.w2 = rb(o.w2); w.b2 = rb(o.b2);
+    w.wqkvP = rbb(o.wqkvP); w.woP = rbb(o.woP); w.wqcP = rbb(o.wqcP); w.wocP = rbb(o.wocP); w.w1P = rbb(o.w1P); w.w2P = rbb(o.w2P);
+    w.wocF = rbb(o.wocF); w.w1iF = rbb(o.w1iF); w.b1i = rb(o.b1i); w.w2kF = rbb(o.w2kF);
+    w.c4_wo = rb(o.c4_wo); w.c4_woc = rb(o.c4_woc); w.c4_w1 = rb(o.c4_w1); w.c4_b1 = rb(o.c4_b1); w.c4_w2 = rb(o.c4_w2);
+  }
+  barrier_.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(barrier_.ptr, 0, 2 * sizeof(unsigned), stream_));
+  nactive_.reserve(1);
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
 Model::~Model() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
@@ -483,6 +550,10 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
   dec_.c4_cs = c4_cs_; dec_.c4_nc = c4_nc_;
+  {
+    const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob: bit mask, default all on
+    dec_.pf_mask = e ? std::atoi(e) : 63;
+  }
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
   {
@@ -1227,6 +1298,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   stage("decoder_finalize", -1, 32);
   times_.decode_steps = steps_launched;
   times_.decode_launches = steps_launched + 1;
+  times_.decoder_version = use_v4 ? 4 : use_v3 ? 3 : use_v2 ? 2 : 1;
   launches += steps_launched + 1;
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
 

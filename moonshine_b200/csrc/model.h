@@ -63,11 +63,15 @@ struct StageTimes {
   int decode_steps = 0;
   int decode_launches = 0;
   int kernel_launches = 0;
+  int decoder_version = 0;   // step kernel that ran: 1, 2, 3 (weight-stationary jobs) or 4 (cluster-resident layers)
 };
 
 class Model {
  public:
   Model(const Dims& dims, const WeightFile& weights, int device);
+  // Replica on another device: the packed weight blob is copied device-to-device (cudaMemcpyPeer: NVLink when the
+  // devices are peers) instead of being rebuilt and uploaded from the host -- the one weight broadcast of SURVEY 8(e).
+  Model(const Model& src, int device);
   ~Model();
 
   const Dims& dims() const { return d_; }

@@ -342,6 +342,15 @@ static Dims dims_for(uint32_t arch, const WeightFile& wf) {
   return dims_from_streaming_config(arch, c.data, c.count);
 }
 
+// "devices": the primary model was built from the host weights on devices[0]; every further device gets a replica
+// whose weights arrive by ONE device-to-device copy of the packed blob (NVLink between peers).  A batch is then cut
+// into contiguous shards, one per device, each decoded by its own host thread; there is no data-path collective.
+void Transcriber::make_replicas() {
+  replicas_.clear();
+  for (size_t i = 1; i < options_.devices.size(); i++) replicas_.push_back(std::make_unique<Model>(*model_, options_.devices[i]));
+  if (!replicas_.empty()) MSB_LOGF("one handle, %zu device contexts (weights replicated device-to-device)", replicas_.size() + 1);
+}
+
 void Transcriber::load_from_directory(const std::string& path) {
   if (options_.skip_transcription) return;
   if (!dir_exists(path)) throw std::runtime_error("Model directory '" + path + "' does not exist");
@@ -361,7 +370,8 @@ void Transcriber::load_from_directory(const std::string& path) {
                                     wf.arch, arch_));
   }
   tokenizer_.reset(Tokenizer::from_file(tpath));
-  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
+  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, options_.devices.empty() ? pick_device(options_.device) : options_.devices[0]);
+  make_replicas();
   if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
   else if (!options_.context.empty()) set_context(options_.context, options_.context_max_terms);
 }
@@ -375,7 +385,8 @@ void Transcriber::load_from_memory(const uint8_t* weights, size_t weights_size,
     throw std::runtime_error(format("model.msw holds architecture %u but %u was requested", wf.arch, arch_));
   }
   tokenizer_ = std::make_unique<Tokenizer>(tokenizer, tokenizer_size);
-  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, pick_device(options_.device));
+  model_ = std::make_unique<Model>(dims_for(arch_, wf), wf, options_.devices.empty() ? pick_device(options_.device) : options_.devices[0]);
+  make_replicas();
   if (!options_.keyterms.empty()) set_keyterms(options_.keyterms);
   else if (!options_.context.empty()) set_context(options_.context, options_.context_max_terms);
 }
@@ -516,10 +527,49 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     StreamPlan plan;
     plan.emitted = plan_emitted.data();
     plan.max_tokens = plan_max_tokens.data();
-    BatchBiasHook bias_hook(biaser_, ptrs.size());
-    model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens,
-                       nullptr, streaming ? &plan : nullptr, options_.word_timestamps ? &xattn : nullptr,
-                       (streaming && !biaser_.empty()) ? &bias_hook : nullptr);
+    const size_t n_dev = std::min(replicas_.size() + 1, ptrs.size());
+    if (n_dev <= 1) {
+      BatchBiasHook bias_hook(biaser_, ptrs.size());
+      model_->transcribe(ptrs.data(), lens.data(), (int)ptrs.size(), options_.max_tokens_per_second, tokens,
+                         nullptr, streaming ? &plan : nullptr, options_.word_timestamps ? &xattn : nullptr,
+                         (streaming && !biaser_.empty()) ? &bias_hook : nullptr);
+    } else {
+      // contiguous shards (sizes differ by at most one), one host thread per device context
+      const size_t n = ptrs.size();
+      std::vector<std::vector<std::vector<int32_t>>> tok_s(n_dev);
+      std::vector<std::vector<CrossAttention>> xa_s(n_dev);
+      std::vector<std::exception_ptr> errs(n_dev);
+      std::vector<std::thread> pool;
+      std::vector<size_t> lo(n_dev + 1, 0);
+      for (size_t d = 0; d < n_dev; d++) lo[d + 1] = lo[d] + n / n_dev + (d < n % n_dev ? 1 : 0);
+      for (size_t d = 0; d < n_dev; d++) {
+        pool.emplace_back([&, d]() {
+          try {
+            Model* m = d == 0 ? model_.get() : replicas_[d - 1].get();
+            const size_t a = lo[d], cnt = lo[d + 1] - lo[d];
+            StreamPlan sp;
+            sp.emitted = streaming ? plan_emitted.data() + a : nullptr;
+            sp.max_tokens = streaming ? plan_max_tokens.data() + a : nullptr;
+            BatchBiasHook hook(biaser_, cnt);
+            m->transcribe(ptrs.data() + a, lens.data() + a, (int)cnt, options_.max_tokens_per_second, tok_s[d], nullptr,
+                          streaming ? &sp : nullptr, options_.word_timestamps ? &xa_s[d] : nullptr,
+                          (streaming && !biaser_.empty()) ? &hook : nullptr);
+          } catch (...) {
+            errs[d] = std::current_exception();
+          }
+        });
+      }
+      for (auto& th : pool) th.join();
+      for (auto& e : errs)
+        if (e) std::rethrow_exception(e);  // a failed device fails the call
+      for (size_t d = 0; d < n_dev; d++) {
+        for (auto& t2 : tok_s[d]) tokens.push_back(std::move(t2));
+        if (options_.word_timestamps) {
+          xa_s[d].resize(lo[d + 1] - lo[d]);
+          for (auto& x : xa_s[d]) xattn.push_back(std::move(x));
+        }
+      }
+    }
     latency_ms = (uint32_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                      std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("MOONSHINE_B200_HOST_PROF"))

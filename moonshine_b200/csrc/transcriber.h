@@ -39,6 +39,7 @@ struct TranscriberOptions {
   std::vector<std::string> keyterms;
   std::string context;
   int device = -1;  // additive option "device": CUDA ordinal (-1 = current / LOCAL_RANK)
+  std::vector<int> devices;  // additive option "devices" ("0,1,2,3" or "all"): one handle fans a batch out over these GPUs
 };
 
 // Segment audio is immutable once published: the segmenter replaces the buffer instead of
@@ -176,6 +177,8 @@ class Transcriber {
   TranscriberOptions options_;
   uint32_t arch_;
   std::unique_ptr<Model> model_;
+  std::vector<std::unique_ptr<Model>> replicas_;  // devices[1..]: weights copied device-to-device from model_
+  void make_replicas();
   std::unique_ptr<Tokenizer> tokenizer_;
   std::mutex model_mutex_;      // serialises model use (reference: stt_model_mutex)
   std::mutex biaser_mutex_;     // reference: context_biaser_mutex, taken before the model mutex

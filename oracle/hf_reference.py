@@ -88,3 +88,24 @@ def time_batched(m, audios, threads):
     t0 = time.perf_counter()
     toks = greedy_batch(m, np.stack(audios), max_len_for(len(audios[0])))
     return time.perf_counter() - t0, toks
+
+
+def pick_threads(m, audios, cores, batch):
+    """The fastest intra-op thread count for this host, found on a SHORT sample (2 s of audio, 6 decode steps, `batch`
+    clips per call): with 65 launches of ~100 small ops per utterance, more threads than the matrices can feed only adds
+    barrier cost (on a 128-core host, 128 threads ran the tiny model 20x slower than 16).  Returns (threads, {t: s})."""
+    import torch
+    cands = sorted({t for t in (4, 8, 16, 32, 64, cores) if 1 <= t <= cores} | {min(cores, 4)})
+    x = np.stack([a[:32000] for a in audios[:batch]])
+    seen = {}
+    for t in cands:
+        torch.set_num_threads(t)
+        greedy_batch(m, x, 2)
+        t0 = time.perf_counter()
+        greedy_batch(m, x, 6)
+        seen[t] = time.perf_counter() - t0
+        if seen[t] > 4 * min(seen.values()):
+            break  # far past the knee: the larger counts only get slower
+    best = min(seen, key=seen.get)
+    torch.set_num_threads(best)
+    return best, seen

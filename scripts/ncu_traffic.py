@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = [("tiny", 32), ("tiny", 1), ("base", 256), ("base_streaming", 64)]
-KERNEL = os.environ.get("NCU_KERNEL", "decoder_step3_kernel")
+KERNEL = os.environ.get("NCU_KERNEL", "decoder_step[34]_kernel")
 
 
 def main():
@@ -24,7 +24,8 @@ def main():
     for model, B in CONFIGS:
         cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
                "-k", f"regex:{KERNEL}", "-s", "30", "-c", "3", "--csv", sys.executable, os.path.join(ROOT, "scripts", "prof_step.py"), model, str(B)]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        env = dict(os.environ, MOONSHINE_B200_V4_COOP="0")  # ncu cannot replay a clustered + cooperative launch
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
         text = r.stdout
         start = text.find('"ID"')
         if start < 0:
@@ -38,8 +39,10 @@ def main():
             unit = row["Metric Unit"].lower()
             scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6}.get(unit, 1)
             per.setdefault(row["ID"], {})[row["Metric Name"]] = v * scale
+        per = {k: v for k, v in per.items() if all(x == x for x in v.values())}  # drop launches ncu could not measure
         n = len(per)
         if n == 0:
+            print("ncu measured no launch for", model, B, file=sys.stderr)
             continue
         rd = sum(p.get("dram__bytes_read.sum", 0) for p in per.values()) / n
         wr = sum(p.get("dram__bytes_write.sum", 0) for p in per.values()) / n
