@@ -231,6 +231,16 @@ MOONSHINE_EXPORT int32_t moonshine_b200_debug_run(
     float *enc_out, uint64_t enc_out_capacity, int32_t *enc_frames, const int32_t *forced,
     int32_t forced_stride, float *logits, int32_t logits_steps, int32_t *out_tokens,
     int32_t out_stride, int32_t *out_counts);
+/* Verify-then-continue decode of a batch (reference: MoonshineStreamingModel::decode_full with speculative_tokens,
+   core/moonshine-streaming-model.cpp:1192-1397; the multi-token decoder run underneath it is decode_tokens'
+   run_decoder_with_cross_kv, :1136-1190).  drafts: [count][draft_stride] ids without BOS / EOS, draft_lens[count]
+   (0 = plain greedy for that utterance).  Eight draft positions per utterance are verified per decoder launch; the
+   returned ids (BOS first, EOS kept when emitted) equal the greedy decode of the same audio whatever the draft holds.
+   out_launches (may be NULL): decoder launches the call took. */
+MOONSHINE_EXPORT int32_t moonshine_b200_decode_with_drafts(
+    int32_t transcriber_handle, const float *const *audio, const uint64_t *lengths, uint64_t count,
+    const int32_t *drafts, int32_t draft_stride, const int32_t *draft_lens, int32_t *out_tokens,
+    int32_t out_stride, int32_t *out_counts, int32_t *out_launches);
 /* Parity hook for the streaming architectures: when enabled, moonshine_b200_debug_run /
    moonshine_b200_transcribe_device treat each utterance as a NON-final update of its segment
    (the encoder's look-ahead features are held back, core/moonshine-streaming-model.cpp:624-626). */

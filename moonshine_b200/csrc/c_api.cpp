@@ -477,6 +477,38 @@ int32_t moonshine_b200_debug_run(int32_t transcriber_handle, const float* const*
   return MOONSHINE_ERROR_NONE;
 }
 
+int32_t moonshine_b200_decode_with_drafts(int32_t transcriber_handle, const float* const* audio, const uint64_t* lengths,
+                                          uint64_t count, const int32_t* drafts, int32_t draft_stride,
+                                          const int32_t* draft_lens, int32_t* out_tokens, int32_t out_stride,
+                                          int32_t* out_counts, int32_t* out_launches) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr || audio == nullptr || lengths == nullptr) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  if (count > 0 && (drafts == nullptr || draft_lens == nullptr || draft_stride < 0)) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  try {
+    std::lock_guard<std::mutex> lock(t->model_mutex());
+    std::vector<const int*> dptr(count, nullptr);
+    std::vector<int> dlen(count, 0);
+    for (uint64_t i = 0; i < count; i++) {
+      if (draft_lens[i] < 0 || draft_lens[i] > draft_stride) return MOONSHINE_ERROR_INVALID_ARGUMENT;
+      dptr[i] = drafts + (size_t)i * draft_stride;
+      dlen[i] = draft_lens[i];
+    }
+    std::vector<std::vector<int32_t>> tokens;
+    t->model()->set_debug_drafts(dptr.data(), dlen.data());
+    t->model()->transcribe(audio, lengths, (int)count, t->options().max_tokens_per_second, tokens, nullptr);
+    if (out_launches) *out_launches = (int32_t)t->model()->last_times().decode_steps;
+    for (uint64_t i = 0; i < count; i++) {
+      const int n = (int)std::min<size_t>(tokens[i].size(), (size_t)std::max(out_stride, 0));
+      if (out_counts) out_counts[i] = (int32_t)tokens[i].size();
+      if (out_tokens) std::memcpy(out_tokens + (size_t)i * out_stride, tokens[i].data(), n * sizeof(int32_t));
+    }
+  } catch (const std::exception& e) {
+    MSB_LOGF("decode_with_drafts failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
 // ---- host-only parity hooks (no GPU needed): the product's own helpers, callable from the CPU tests that
 // compare them with a build of the reference's own sources ----
 int64_t moonshine_b200_debug_tokens_to_text(const uint8_t* tokenizer, uint64_t tokenizer_size, const int32_t* ids,

@@ -665,6 +665,7 @@ __device__ __forceinline__ int step_prologue_warp(const DecoderParams& p, int b,
   const int64_t row = (int64_t)b * (p.Smax + 1);
   int tok_in;
   bool finished;
+  if (p.row_tok) return min(max(__ldg(p.row_tok + b), 0), p.V - 1);  // explicit rows: the host-side plan kernel keeps the books
   if (p.step == 0) {
     tok_in = p.forced ? p.forced[row] : p.tokens[row];
     finished = p.max_len[b] <= 0;
@@ -682,6 +683,12 @@ __device__ __forceinline__ int step_prologue_warp(const DecoderParams& p, int b,
   return tok_in;
 }
 
+// explicit rows (see DecoderParams): position, utterance and in-launch predecessors of row b
+__device__ __forceinline__ int row_position(const DecoderParams& p, int b) { return p.row_pos ? __ldg(p.row_pos + b) : p.step; }
+__device__ __forceinline__ int row_utterance(const DecoderParams& p, int b) { return p.row_utt ? __ldg(p.row_utt + b) : b; }
+__device__ __forceinline__ int row_inlaunch(const DecoderParams& p, int b) { return p.row_nin ? __ldg(p.row_nin + b) : 0; }
+__device__ __forceinline__ int cache_utts(const DecoderParams& p) { return p.row_utt ? p.B_utt : p.B; }
+
 __device__ __forceinline__ bool tile_active(const DecoderParams& p, const unsigned char* active, int nb, int b0) {
   bool any = false;
   for (int b = 0; b < nb; b++) any |= (b0 + b < p.B) && active[b0 + b];
@@ -693,7 +700,7 @@ __device__ __forceinline__ void load_flags(const DecoderParams& p, const Ctx& c,
     const int b = b0 + threadIdx.x;
     const bool live = threadIdx.x < nb && b < p.B && c.active[b];
     c.flags[threadIdx.x] = live ? 0 : 1;
-    if (with_enc_len) c.flags[32 + threadIdx.x] = live ? p.enc_len[b] : 0;
+    if (with_enc_len) c.flags[32 + threadIdx.x] = live ? p.enc_len[row_utterance(p, b)] : 0;
   }
   csync();
 }
@@ -713,10 +720,10 @@ __device__ __forceinline__ void produce_self(const DecoderParams& p, int l, int 
   // The self K/V prefix is read straight from global by the warp that owns the utterance (a few KB per item,
   // written by earlier launches -- walking it through the CTA-wide ring serialised the 8 warps).  It has left L2
   // since (one step streams more than L2 holds): ask L2 for it now, a phase ahead of its use.
-  if (p.step > 0 && ring.turn == 0) {
+  if (p.step > 0 && ring.turn == 0 && p.row_pos == nullptr) {
     for (int b = 0; b < nb; b++) {
       if (b0 + b >= p.B || !active[b0 + b]) continue;
-      const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+      const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
       const float* kt = p.ks + bh * hd * p.Smax;
       const float* vr = p.vs + bh * p.Smax * hd;
       const uint32_t kbytes = (uint32_t)(hd * p.Smax * 4), vbytes = (uint32_t)((p.step * hd * 4 + 15) & ~15);
@@ -820,8 +827,12 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
       const int r = i - b * 2 * half_rot;
       const int which = r / half_rot;
       const int pr = r - which * half_rot;
-      const float cs = c.rope[pr];
-      const float sn = c.rope[64 + pr];
+      float cs = c.rope[pr], sn = c.rope[64 + pr];
+      if (p.row_pos && b0 + b < p.B) {  // explicit rows: every row has its own position
+        const int64_t at = (int64_t)__ldg(p.row_pos + b0 + b) * half_rot + pr;
+        cs = __ldg(p.rope_cos + at);
+        sn = __ldg(p.rope_sin + at);
+      }
       float* v = c.act + b * actw + which * hd + 2 * pr;
       const float x0 = v[0], x1 = v[1];
       v[0] = x0 * cs - x1 * sn;
@@ -832,9 +843,10 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
   for (int i = threadIdx.x; i < nb * hd; i += kConsumers) {  // K/V append at position `step`
     const int b = i / hd, d = i - b * hd;
     if (!c.flags[b]) {
-      const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
-      p.ks[(bh * hd + d) * p.Smax + p.step] = c.act[b * actw + hd + d];
-      p.vs[(bh * p.Smax + p.step) * hd + d] = c.act[b * actw + 2 * hd + d];
+      const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
+      const int pos = row_position(p, b0 + b);
+      p.ks[(bh * hd + d) * p.Smax + pos] = c.act[b * actw + hd + d];
+      p.vs[(bh * p.Smax + pos) * hd + d] = c.act[b * actw + 2 * hd + d];
     }
   }
   // causal self-attention: ONE WARP per utterance (round-robin), warp-level syncs only.  The cached prefix
@@ -850,17 +862,18 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
       owner = (owner + 1) & (kWarpsC - 1);
       if (!mine) continue;
       const float* q = c.act + b * actw;
-      const float* kcur = q + hd;
-      const float* vcur = q + 2 * hd;
-      const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+      // keys: cached positions [0, base) from global memory (written by earlier launches), then the rows of this launch
+      // that precede the row inside its utterance (explicit rows: nin of them, straight from shared memory) and itself
+      const int pos = row_position(p, b0 + b), nin = min(row_inlaunch(p, b0 + b), b), base = pos - nin;
+      const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
       const float* Kt = p.ks + bh * hd * p.Smax;
       const float* Vr = p.vs + bh * p.Smax * hd;
       float mx = -INFINITY;
       // scores: two key positions per lane, 12 head dims per trip = 24 independent loads in flight per lane (the
       // chain is memory-latency bound: the prefix was written by earlier launches and has left L2 since)
-      for (int t0 = 0; t0 < p.step; t0 += 64) {
+      for (int t0 = 0; t0 < base; t0 += 64) {
         const int ta = t0 + lane, tb = t0 + 32 + lane;
-        const bool va = ta < p.step, vb = tb < p.step;
+        const bool va = ta < base, vb = tb < base;
         float sa = 0.f, sb = 0.f;
 #pragma unroll 1
         for (int d0 = 0; d0 < hd; d0 += 12) {
@@ -881,18 +894,19 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
         if (va) { sa *= scale; sc[ta] = sa; mx = fmaxf(mx, sa); }
         if (vb) { sb *= scale; sc[tb] = sb; mx = fmaxf(mx, sb); }
       }
-      {
+      for (int j = 0; j <= nin; j++) {
+        const float* kj = c.act + (b - nin + j) * actw + hd;
         float s = 0.f;
-        for (int d = lane; d < hd; d += 32) s = fmaf(q[d], kcur[d], s);
+        for (int d = lane; d < hd; d += 32) s = fmaf(q[d], kj[d], s);
         s = warp_sum(s) * scale;
-        if (lane == 0) sc[p.step] = s;
+        if (lane == 0) sc[base + j] = s;
         mx = fmaxf(mx, s);
       }
       mx = warp_max(mx);
       __syncwarp();
       prof_mark(c, 66);
       float sum = 0.f;
-      for (int t = lane; t <= p.step; t += 32) {
+      for (int t = lane; t <= pos; t += 32) {
         const float e = expf(sc[t] - mx);
         sc[t] = e;
         sum += e;
@@ -905,7 +919,7 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
         const bool has0 = lane < hd, has1 = lane + 32 < hd;
         int t = 0;
 #pragma unroll 1
-        for (; t + 16 <= p.step; t += 16) {  // 16 rows (32 loads) per trip
+        for (; t + 16 <= base; t += 16) {  // 16 rows (32 loads) per trip
           float v0[16], v1[16];
 #pragma unroll
           for (int u = 0; u < 16; u++) {
@@ -920,7 +934,7 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
           }
         }
 #pragma unroll 1
-        for (; t + 8 <= p.step; t += 8) {  // 8 rows (16 loads) per trip
+        for (; t + 8 <= base; t += 8) {  // 8 rows (16 loads) per trip
           float v0[8], v1[8];
 #pragma unroll
           for (int u = 0; u < 8; u++) {
@@ -934,15 +948,20 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
             o1 = fmaf(pt, v1[u], o1);
           }
         }
-        for (; t < p.step; t++) {
+        for (; t < base; t++) {
           const float pt = sc[t];
           if (has0) o0 = fmaf(pt, __ldg(Vr + (int64_t)t * hd + lane), o0);
           if (has1) o1 = fmaf(pt, __ldg(Vr + (int64_t)t * hd + lane + 32), o1);
         }
       }
-      const float pl = sc[p.step];
-      if (lane < hd) c.att[b * attw + lane] = fmaf(pl, vcur[lane], o0) * inv;
-      if (lane + 32 < hd) c.att[b * attw + lane + 32] = fmaf(pl, vcur[lane + 32], o1) * inv;
+      for (int j = 0; j <= nin; j++) {
+        const float* vj = c.act + (b - nin + j) * actw + 2 * hd;
+        const float pl = sc[base + j];
+        if (lane < hd) o0 = fmaf(pl, vj[lane], o0);
+        if (lane + 32 < hd) o1 = fmaf(pl, vj[lane + 32], o1);
+      }
+      if (lane < hd) c.att[b * attw + lane] = o0 * inv;
+      if (lane + 32 < hd) c.att[b * attw + lane + 32] = o1 * inv;
     }
   }
   prof_mark(c, 68);
@@ -979,7 +998,7 @@ __device__ __forceinline__ void produce_cross(const DecoderParams& p, int l, int
   if (p.pf_mask & 32) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   auto ask = [&](int b) {
     if (b >= nb || b0 + b >= p.B || !active[b0 + b]) return;
-    const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+    const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
     l2_prefetch(p.kc + bh * hd * p.Tpad, kv_bytes);
     l2_prefetch(p.vc + bh * p.Tpad * hd, kv_bytes);
   };
@@ -989,7 +1008,7 @@ __device__ __forceinline__ void produce_cross(const DecoderParams& p, int l, int
   for (int b = 0; b < nb; b++) {
     if (window) ask(b + kCrossWindow);
     if (b0 + b >= p.B || !active[b0 + b]) continue;
-    const int64_t bh = ((int64_t)l * p.B + (b0 + b)) * H + h;
+    const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
     produce_block_f16(ring, p.kc + bh * hd * p.Tpad, hd, p.Tpad, pol);   // K^T [hd][Tpad]
     produce_block_f16(ring, p.vc + bh * p.Tpad * hd, p.Tpad, hd, pol);   // V   [Tpad][hd]
   }
@@ -1534,8 +1553,12 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
 
   // work list of this launch: utterances not finished BEFORE this step (done[b] = step at which it finished + 1)
   for (int b = threadIdx.x; b < p.B; b += kThreads3) {
-    const int d = p.done[b];
-    active[b] = (d == 0 || d > p.step) ? 1 : 0;
+    if (p.row_tok) {  // explicit rows: the plan kernel decided which rows run
+      active[b] = p.row_tok[b] >= 0 ? 1 : 0;
+    } else {
+      const int d = p.done[b];
+      active[b] = (d == 0 || d > p.step) ? 1 : 0;
+    }
   }
   const unsigned epoch = *reinterpret_cast<const volatile unsigned*>(p.sync3);
   uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 33);
@@ -1696,11 +1719,12 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
     if (threadIdx.x == 0) *cnt = 0;
     csync();
     int n = 0;
-    for (int b = threadIdx.x; b < p.B; b += kConsumers) n += __ldcg(p.done + b) ? 0 : 1;
+    if (p.row_tok == nullptr)
+      for (int b = threadIdx.x; b < p.B; b += kConsumers) n += __ldcg(p.done + b) ? 0 : 1;
     if (n) atomicAdd(cnt, n);
     csync();
     if (threadIdx.x == 0) {
-      *p.n_active = *cnt;
+      if (p.row_tok == nullptr) *p.n_active = *cnt;  // explicit rows: the plan kernel counts
       p.sync3[0] = epoch + 1u;
     }
   }
@@ -1719,7 +1743,78 @@ __global__ void decoder_resolve_kernel(const __grid_constant__ DecoderParams p, 
   if ((threadIdx.x & 31) == 0) out[b] = tok;
 }
 
+// Plan of explicit-row launch k of a verify-then-continue decode (reference: decode_full,
+// core/moonshine-streaming-model.cpp:1192-1397, batched and chunked: n rows per utterance per launch instead of the
+// whole draft in one decoder run).  One warp per utterance: resolves the argmax of the rows launch k-1 ran for it,
+// books the emitted ids exactly like the greedy loop would (ids, EOS / budget stop), advances the utterance
+//   VERIFY  inputs [BOS, draft...] at positions pos .. pos+n-1 (row i also attends the i rows before it); an emitted
+//           id that equals the next draft id keeps verifying, anything else (or the end of the draft) -> AR
+//   AR      one row: the last emitted id at its own position (utterances diverge at different positions)
+//   DONE    EOS emitted or the budget reached
+// and writes the rows of launch k.  Rows behind a rejected draft id computed K/V for positions the utterance re-writes
+// before it ever reads them (position p is appended by the row at p before any row attends it), so nothing is reset.
+__global__ void decoder_verify_plan_kernel(const __grid_constant__ DecoderParams p, VerifyState s, int k, int n, int bos, int eos) {
+  __shared__ int alive;
+  if (threadIdx.x == 0) alive = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int* row_tok = const_cast<int*>(p.row_tok);
+  int* row_pos = const_cast<int*>(p.row_pos);
+  int* row_nin = const_cast<int*>(p.row_nin);
+  int* row_utt = const_cast<int*>(p.row_utt);
+  for (int u = warp; u < p.B_utt; u += nw) {
+    int mode = s.mode[u], pos = s.pos[u], cur = s.cur[u];
+    const int prevn = s.prev_n[u], m = s.draft_len[u], maxlen = p.max_len[u];
+    const int* d = s.draft + (int64_t)u * s.draft_stride;
+    const int64_t trow = (int64_t)u * (p.Smax + 1);
+    if (k == 0) {
+      mode = maxlen > 0 ? (m > 0 ? 0 : 1) : 2;
+      pos = 0;
+      cur = bos;
+    } else if (mode != 2) {
+      for (int i = 0; i < prevn; i++) {
+        const int e = resolve_token_warp(p, u * n + i, (k - 1) & 1);
+        const int t = pos + i;
+        if (lane == 0) {
+          p.tokens[trow + t + 1] = e;
+          p.n_tokens[u] = t + 2;
+        }
+        if (e == eos || t + 1 >= maxlen) { mode = 2; break; }
+        const bool accepted = mode == 0 && t < m && e == d[t];
+        if (accepted && i + 1 < prevn) continue;
+        if (!accepted) { mode = 1; cur = e; }
+        pos = t + 1;
+        break;
+      }
+    }
+    int rows = 0;
+    if (mode == 0) rows = min(n, min(m + 1 - pos, maxlen - pos));
+    else if (mode == 1) rows = 1;
+    if (lane < n) {
+      const int r = u * n + lane;
+      const bool on = lane < rows;
+      const int at = pos + lane;
+      row_tok[r] = !on ? -1 : (mode == 1 ? cur : (at == 0 ? bos : d[at - 1]));
+      row_pos[r] = on ? at : 0;
+      row_nin[r] = on && mode == 0 ? lane : 0;
+      row_utt[r] = u;
+    }
+    if (lane == 0) {
+      s.mode[u] = mode; s.pos[u] = pos; s.cur[u] = cur; s.prev_n[u] = rows;
+      if (mode != 2) atomicAdd(&alive, 1);
+      else p.done[u] = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *p.n_active = alive;
+}
+
 }  // namespace
+
+void launch_decoder_verify_plan(const DecoderParams& p, const VerifyState& s, int k, int n, int bos, int eos, cudaStream_t stream) {
+  if (n < 1 || n > 16) throw std::runtime_error("decoder v3: 1..16 rows per utterance");
+  decoder_verify_plan_kernel<<<1, 1024, 0, stream>>>(p, s, k, n, bos, eos);
+}
 
 void launch_decoder_resolve(const DecoderParams& p, int* out, cudaStream_t stream) {
   const int warps_per_block = 4;
@@ -1747,6 +1842,10 @@ void decoder_step3_plan(DecoderParams& p, int grid) {
   p.nb_cross = pick(128);
   p.nb_self = std::max(pick(128), std::min(8, p.nb_cross * 4));
   if (p.nb_self > kMaxNB) p.nb_self = kMaxNB;
+  if (p.row_group > 1) {  // explicit rows: the rows of one utterance slot share a self-attention tile
+    if (p.row_group > kMaxNB || (kMaxNB % p.row_group) != 0) throw std::runtime_error("decoder v3: row group must divide 16");
+    while (p.nb_self % p.row_group) p.nb_self *= 2;
+  }
   p.nb_self = env_int("MOONSHINE_B200_NB_SELF", p.nb_self);
   p.nb_cross = env_int("MOONSHINE_B200_NB_CROSS", p.nb_cross);
   auto pow2_le16 = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8 || v == 16; };

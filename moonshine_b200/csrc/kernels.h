@@ -216,6 +216,16 @@ struct DecoderParams {
   // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
   int c4_cs, c4_nc, c4_u;     // v4: cluster size, clusters, utterances per cluster
   int pf_mask;                // L2 prefetch pipelines: v4 bit 0 weights, 1 cross K/V, 2 vocabulary slab; v3 bit 3 next-phase weights, 4 cross K/V window, 5 evict-first K/V
+  // ---- explicit rows (v3 only; multi-token verify and per-utterance positions; reference: run_decoder_with_cross_kv
+  // fed n > 1 tokens by decode_tokens / decode_full, core/moonshine-streaming-model.cpp:1136-1190, 1192-1397).  A row is
+  // one (utterance, position) pair; rows of one utterance are consecutive, ascending in position, and never straddle a
+  // self-attention tile.  All null = row b is utterance b at position `step` (the lockstep greedy loop).
+  const int* row_tok;         // [B] input id of the row; < 0: the row idles this launch
+  const int* row_pos;         // [B] decode position (RoPE, K/V append slot, attention length - 1)
+  const int* row_nin;         // [B] how many rows directly before this one belong to the same utterance in THIS launch
+  const int* row_utt;         // [B] utterance of the row (self / cross caches, encoder length)
+  int B_utt;                  // utterances behind the caches (= B when the row arrays are null)
+  int row_group;              // rows per utterance slot (self-attention tiles hold a multiple of it)
   const float* bias_static;   // [V] bonus shared by every utterance and step (the trie root's children)
   const int* bias_dyn_n;      // [B] per-utterance entries of this step
   const int* bias_dyn_ids;    // [B][bias_dyn_cap] token ids
@@ -224,6 +234,18 @@ struct DecoderParams {
 };
 constexpr int kSync3Words = 32 + 32 * 64;
 void launch_decoder_step3(const DecoderParams& p, int grid, cudaStream_t stream);
+// explicit-row decoding (v3): per-utterance state of a verify-then-continue decode, all device pointers
+struct VerifyState {
+  int* mode;             // [B_utt] 0 verifying the draft, 1 auto-regressive, 2 done
+  int* pos;              // [B_utt] next position to feed
+  int* cur;              // [B_utt] next input id in auto-regressive mode
+  int* prev_n;           // [B_utt] rows the previous launch ran for the utterance
+  const int* draft;      // [B_utt][draft_stride] draft ids (no BOS / EOS)
+  const int* draft_len;  // [B_utt]
+  int draft_stride;
+};
+// books launch k-1 and writes the rows of launch k (p: explicit-row parameters, p.B = B_utt * n rows)
+void launch_decoder_verify_plan(const DecoderParams& p, const VerifyState& s, int k, int n, int bos, int eos, cudaStream_t stream);
 size_t decoder_step3_smem_bytes(const DecoderParams& p);
 // fills nb_self / nb_cross / nx / job_first / job_ncta for batch size p.B on a grid of `grid` CTAs
 void decoder_step3_plan(DecoderParams& p, int grid);

@@ -551,8 +551,8 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
   dec_.c4_cs = c4_cs_; dec_.c4_nc = c4_nc_;
   {
-    const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob: bit mask, default all on
-    dec_.pf_mask = e ? std::atoi(e) : 63;
+    const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob (bit mask, see DecoderParams::pf_mask); off by default: measured neutral or slightly negative at tiny/32 and base/256 (profiles/r2e_prefetch_ab.txt)
+    dec_.pf_mask = e ? std::atoi(e) : 0;
   }
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
@@ -1074,7 +1074,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   tokens_dev_.reserve((size_t)B * (Smax + 1));
   ntok_dev_.reserve(B);
   done_dev_.reserve(B);
-  pin_tokens_.reserve((size_t)B * (Smax + 1) + B + 2);
+  pin_tokens_.reserve((size_t)B * (Smax + 1) + 2 * (size_t)B + 4);
   {
     int* ht = pin_tokens_.ptr;
     int* hn = ht + (size_t)B * (Smax + 1);
@@ -1154,7 +1154,76 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   }
   std::vector<std::vector<int32_t>> hooked_tokens;  // filled by the host-stepped loop
   int steps_launched = max_steps;
-  if (hook == nullptr) {
+  bool any_draft = false;
+  const int* const* drafts = (plan && plan->draft && plan->draft_len) ? plan->draft : dbg_draft_;
+  const int* draft_lens = (plan && plan->draft && plan->draft_len) ? plan->draft_len : dbg_draft_len_;
+  dbg_draft_ = nullptr;
+  dbg_draft_len_ = nullptr;
+  if (drafts && draft_lens)
+    for (int b = 0; b < B; b++) any_draft |= drafts[b] != nullptr && draft_lens[b] > 0;
+  const bool verify = any_draft && hook == nullptr && xattn == nullptr && dbg == nullptr && use_v3 && max_steps > 0 &&
+                      B * kVerifyRows <= 4096;
+  if (verify) {
+    // ---- verify-then-continue on explicit rows (decode_full, moonshine-streaming-model.cpp:1192-1397) ----
+    // kVerifyRows consecutive draft positions of every utterance per launch; the plan kernel between two launches books
+    // the emitted ids and moves each utterance on (verify -> auto-regressive -> done).  An accepted draft of m ids
+    // costs ceil((m + 1) / kVerifyRows) launches instead of m + 1.
+    const int n = kVerifyRows, R = B * n;
+    DecoderParams q = p;
+    q.B = R; q.B_utt = B; q.row_group = n;
+    hbuf_.reserve((size_t)2 * R * D);
+    part_.reserve((size_t)std::max(2 * H + q.n_chunk, H + q.ffn_ksplit + 1) * R * D);
+    attc_.reserve((size_t)R * D);
+    act_.reserve((size_t)R * I);
+    xfin_.reserve((size_t)R * D);
+    cand_val_.reserve((size_t)2 * q.n_vchunk * R);
+    cand_idx_.reserve((size_t)2 * q.n_vchunk * R);
+    rows_dev_.reserve((size_t)4 * R);
+    vstate_dev_.reserve((size_t)4 * B);
+    const int dstride = Smax + 1;
+    draft_dev_.reserve((size_t)B * dstride + B);
+    q.hbuf = hbuf_.ptr; q.part = part_.ptr; q.attc = attc_.ptr; q.act = act_.ptr; q.xfin = xfin_.ptr;
+    q.cand_val = cand_val_.ptr; q.cand_idx = cand_idx_.ptr;
+    q.row_tok = rows_dev_.ptr; q.row_pos = rows_dev_.ptr + R; q.row_nin = rows_dev_.ptr + 2 * R; q.row_utt = rows_dev_.ptr + 3 * R;
+    q.logits_out = nullptr; q.xattn_out = nullptr; q.forced = nullptr; q.prof = nullptr;
+    std::vector<int> hd_((size_t)B * dstride + B, 0);
+    int m_max = 0;
+    for (int b = 0; b < B; b++) {
+      const int m = drafts[b] ? std::min(std::max(draft_lens[b], 0), Smax - 1) : 0;
+      for (int i = 0; i < m; i++) hd_[(size_t)b * dstride + i] = drafts[b][i];
+      hd_[(size_t)B * dstride + b] = m;
+      m_max = std::max(m_max, m);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(draft_dev_.ptr, hd_.data(), hd_.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemsetAsync(vstate_dev_.ptr, 0, (size_t)4 * B * sizeof(int), stream_));
+    VerifyState st;
+    st.mode = vstate_dev_.ptr; st.pos = vstate_dev_.ptr + B; st.cur = vstate_dev_.ptr + 2 * B; st.prev_n = vstate_dev_.ptr + 3 * B;
+    st.draft = draft_dev_.ptr; st.draft_len = draft_dev_.ptr + (size_t)B * dstride; st.draft_stride = dstride;
+    decoder_step3_plan(q, grid);
+    int k = 0;
+    auto run_steps = [&](int count) {
+      for (int i = 0; i < count; i++, k++) {
+        q.step = k;
+        launch_decoder_step3(q, grid, stream_);
+        launch_decoder_verify_plan(q, st, k + 1, n, d_.bos, d_.eos, stream_);
+      }
+    };
+    launch_decoder_verify_plan(q, st, 0, n, d_.bos, d_.eos, stream_);
+    run_steps(std::min((m_max + 1 + n - 1) / n, max_steps));
+    // every draft is now either verified to its end or rejected: what is left is one id per launch and utterance
+    int* hn = pin_tokens_.ptr + (size_t)B * (Smax + 1);
+    while (true) {
+      CUDA_CHECK(cudaMemcpyAsync(hn, ntok_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(hn + B, vstate_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));  // modes
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      int rem = 0;
+      for (int b = 0; b < B; b++)
+        if (hn[B + b] != 2) rem = std::max(rem, mlen[b] - (hn[b] - 1));
+      if (rem <= 0) break;
+      run_steps(std::min(rem, 16));  // bounded bursts: an EOS ends the tail early, the next read sees it
+    }
+    steps_launched = k;
+  } else if (hook == nullptr) {
     for (int t = 0; t < max_steps; t++) {
       p.step = t;
       p.prof = (t == prof_step) ? (void*)prof_buf.ptr : nullptr;
@@ -1293,9 +1362,11 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       fprintf(stderr, "\n");
     }
   }
-  p.step = max_steps;
-  launch_decoder_finalize(p, stream_);
-  stage("decoder_finalize", -1, 32);
+  if (!verify) {
+    p.step = max_steps;
+    launch_decoder_finalize(p, stream_);
+    stage("decoder_finalize", -1, 32);
+  }
   times_.decode_steps = steps_launched;
   times_.decode_launches = steps_launched + 1;
   times_.decoder_version = use_v4 ? 4 : use_v3 ? 3 : use_v2 ? 2 : 1;

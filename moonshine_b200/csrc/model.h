@@ -33,7 +33,13 @@ struct DebugCapture {
 struct StreamPlan {
   const int* emitted = nullptr;     // [B] encoder features that form the decoder memory (<= analysed / 320)
   const int* max_tokens = nullptr;  // [B] decode budget
+  // Speculative drafts (reference: decode_full's speculative_tokens, moonshine-streaming-model.cpp:1192-1197): the ids
+  // of the previous decode of the same open segment, no BOS / EOS.  Verified kVerifyRows positions per launch on the
+  // explicit-row decoder; the result equals the greedy decode id for id.  Null / length 0 = plain greedy.
+  const int* const* draft = nullptr;  // [B] host pointers
+  const int* draft_len = nullptr;     // [B]
 };
+constexpr int kVerifyRows = 8;  // draft positions verified per utterance per launch
 
 // Decoder cross-attention of one utterance, as align_words consumes it: [layers * heads][steps][frames]
 // (layer-major), steps = decoder runs = generated ids, frames = encoder memory length.
@@ -99,6 +105,8 @@ class Model {
   void set_timing(bool on) { timing_ = on; }
   // parity hook: plan-less calls on a streaming model act as a NON-final update (look-ahead held back)
   void set_debug_stream_partial(bool on) { debug_stream_partial_ = on; }
+  // speculative drafts for the next transcribe() whose plan carries none (moonshine_b200_decode_with_drafts)
+  void set_debug_drafts(const int* const* draft, const int* len) { dbg_draft_ = draft; dbg_draft_len_ = len; }
   size_t weight_bytes() const { return wblob_.bytes(); }
 
  private:
@@ -165,6 +173,9 @@ class Model {
   PinnedBuffer<int> pin_bias_i32_;
   PinnedBuffer<float> pin_bias_f32_;
   DeviceBuffer<int> nactive_;
+  DeviceBuffer<int> rows_dev_, vstate_dev_, draft_dev_;  // explicit-row decoding (speculative verify)
+  const int* const* dbg_draft_ = nullptr;                // drafts for the NEXT run() when its plan carries none (test entry)
+  const int* dbg_draft_len_ = nullptr;
   PinnedBuffer<int> pin_i32_;
   PinnedBuffer<int64_t> pin_i64_;
   PinnedBuffer<float> pin_pcm_;

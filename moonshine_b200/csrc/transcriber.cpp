@@ -456,6 +456,8 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
   std::vector<const float*> ptrs;
   std::vector<uint64_t> lens;
   std::vector<int> plan_emitted, plan_max_tokens;   // streaming architectures only
+  std::vector<const int*> plan_draft;                // speculative drafts (previous ids of the same open segment)
+  std::vector<int> plan_draft_len;
   const bool streaming = model_ && model_->dims().streaming;
   for (size_t j = 0; j < jobs.size(); j++) {
     jobs[j].output->clear_update_flags();
@@ -498,7 +500,14 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
             const float dur = (float)s.stream_emitted * 0.020f;
             budget = std::min((int)std::ceil((double)dur * 6.5), model_->dims().max_seq_len);
             p.strip_eos = true;
+            // (MOONSHINE_B200_SPEC_VERIFY=0: same budgets, plain greedy launches -- the A/B switch of the tests)
+            const char* off = std::getenv("MOONSHINE_B200_SPEC_VERIFY");
+            const bool use_draft = !(off && off[0] == '0') && !s.stream_tokens.empty();
+            plan_draft.push_back(use_draft ? s.stream_tokens.data() : nullptr);
+            plan_draft_len.push_back(use_draft ? (int)s.stream_tokens.size() : 0);
           } else {
+            plan_draft.push_back(nullptr);
+            plan_draft_len.push_back(0);
             const float dur = (float)L / (float)kSampleRate;
             budget = std::min((int)std::ceil(dur * options_.max_tokens_per_second), 256);
           }
@@ -527,6 +536,8 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
     StreamPlan plan;
     plan.emitted = plan_emitted.data();
     plan.max_tokens = plan_max_tokens.data();
+    plan.draft = plan_draft.data();
+    plan.draft_len = plan_draft_len.data();
     const size_t n_dev = std::min(replicas_.size() + 1, ptrs.size());
     if (n_dev <= 1) {
       BatchBiasHook bias_hook(biaser_, ptrs.size());
@@ -550,6 +561,8 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
             StreamPlan sp;
             sp.emitted = streaming ? plan_emitted.data() + a : nullptr;
             sp.max_tokens = streaming ? plan_max_tokens.data() + a : nullptr;
+            sp.draft = streaming ? plan_draft.data() + a : nullptr;
+            sp.draft_len = streaming ? plan_draft_len.data() + a : nullptr;
             BatchBiasHook hook(biaser_, cnt);
             m->transcribe(ptrs.data() + a, lens.data() + a, (int)cnt, options_.max_tokens_per_second, tok_s[d], nullptr,
                           streaming ? &sp : nullptr, options_.word_timestamps ? &xa_s[d] : nullptr,
@@ -583,6 +596,11 @@ void Transcriber::update_outputs(std::vector<Job>& jobs) {
       const size_t utt = ti;
       std::vector<int32_t>& ids = tokens[ti++];
       if (p.strip_eos && !ids.empty() && ids.back() == model_->dims().eos) ids.pop_back();
+      if (streaming) {  // the next update of this (still open) segment verifies these ids instead of re-deriving them
+        s.stream_tokens.clear();
+        for (int32_t id : ids)
+          if (id != model_->dims().bos && id != model_->dims().eos) s.stream_tokens.push_back(id);
+      }
       // Word timestamps from the cross-attention the decode just produced.  Classic architectures align
       // complete lines only (core/transcriber.cpp:1103-1117), the streaming path every decode (:1029-1070);
       // time per frame = segment duration / memory frames, times offset by the segment start.

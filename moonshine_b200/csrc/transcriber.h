@@ -61,6 +61,8 @@ struct Segment {
   int stream_emitted = 0;
   bool stream_decoded = false;
   uint64_t stream_keyterm_epoch = 0;  // key-term list the last decode ran under
+  std::vector<int32_t> stream_tokens; // content ids of the last decode (no BOS / EOS): the next update's speculative draft
+                                      // (last_streaming_tokens, core/transcriber.cpp:1403-1412, 1475)
 };
 
 // The reference's VoiceActivityDetector (core/voice-activity-detector.cpp)
