@@ -241,6 +241,13 @@ MOONSHINE_EXPORT int32_t moonshine_b200_decode_with_drafts(
     int32_t transcriber_handle, const float *const *audio, const uint64_t *lengths, uint64_t count,
     const int32_t *drafts, int32_t draft_stride, const int32_t *draft_lens, int32_t *out_tokens,
     int32_t out_stride, int32_t *out_counts, int32_t *out_launches);
+/* Teacher-forced multi-token decoder runs (reference: MoonshineStreamingModel::decode_tokens,
+   core/moonshine-streaming-model.cpp:1136-1190, batched): tokens [count][tokens_stride] ids incl. the start id; the
+   first n_steps positions of every utterance go through the decoder rows_per_launch (2..16) positions per launch;
+   logits_out [n_steps][count][V] receives the logits of every position (rows beyond an utterance's budget stay 0). */
+MOONSHINE_EXPORT int32_t moonshine_b200_decode_tokens(
+    int32_t transcriber_handle, const float *const *audio, const uint64_t *lengths, uint64_t count,
+    const int32_t *tokens, int32_t tokens_stride, int32_t n_steps, int32_t rows_per_launch, float *logits_out);
 /* Parity hook for the streaming architectures: when enabled, moonshine_b200_debug_run /
    moonshine_b200_transcribe_device treat each utterance as a NON-final update of its segment
    (the encoder's look-ahead features are held back, core/moonshine-streaming-model.cpp:624-626). */

@@ -107,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "moonshine_free_grapheme_to_phonemizer", "moonshine_text_to_phonemes",
     "moonshine_transcribe_batch_without_streaming", "moonshine_b200_transcribe_device",
     "moonshine_b200_get_stream", "moonshine_b200_set_timing", "moonshine_b200_last_timings",
-    "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial", "moonshine_b200_decode_with_drafts",
+    "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial", "moonshine_b200_decode_with_drafts", "moonshine_b200_decode_tokens",
     "moonshine_b200_debug_tokens_to_text", "moonshine_b200_debug_resample", "moonshine_b200_debug_align_words", "moonshine_b200_test_ring_bandwidth",
     "moonshine_b200_debug_text_to_tokens", "moonshine_b200_debug_biaser_apply", "moonshine_b200_debug_biaser_apply_sparse", "moonshine_b200_debug_extract_terms", "moonshine_b200_test_gemm",
 ]
@@ -206,6 +206,9 @@ def load_library() -> ctypes.CDLL:
     lib.moonshine_b200_decode_with_drafts.restype = c.c_int32
     lib.moonshine_b200_decode_with_drafts.argtypes = [
         c.c_int32, c.POINTER(f32p), u64p, c.c_uint64, i32p, c.c_int32, i32p, i32p, c.c_int32, i32p, i32p]
+    lib.moonshine_b200_decode_tokens.restype = c.c_int32
+    lib.moonshine_b200_decode_tokens.argtypes = [
+        c.c_int32, c.POINTER(f32p), u64p, c.c_uint64, i32p, c.c_int32, c.c_int32, c.c_int32, f32p]
     lib.moonshine_b200_test_gemm.restype = c.c_int32
     lib.moonshine_b200_test_gemm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p] + [c.c_int32] * 6 + [c.c_void_p] + [c.c_int32] * 3
     _lib = lib
@@ -456,6 +459,21 @@ class Transcriber:
             toks.ctypes.data_as(i32p), max_tokens, cnt.ctypes.data_as(i32p), ctypes.byref(launches))
         _check(rc, "decode_with_drafts failed")
         return [toks[i, :min(cnt[i], max_tokens)].tolist() for i in range(n)], int(launches.value)
+
+
+    def decode_tokens(self, audios: Sequence, tokens: np.ndarray, vocab: int, n_steps: int, rows_per_launch: int = 8):
+        """Teacher-forced multi-token decoder runs (reference: decode_tokens): logits [n_steps, B, V]."""
+        arrs = [_as_f32(a) for a in audios]
+        n = len(arrs)
+        ptrs = (ctypes.POINTER(ctypes.c_float) * n)(*[a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for a in arrs])
+        lens = (ctypes.c_uint64 * n)(*[a.size for a in arrs])
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        lg = np.zeros((n_steps, n, vocab), np.float32)
+        rc = self._lib.moonshine_b200_decode_tokens(
+            self._handle, ptrs, lens, n, tokens.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), tokens.shape[1], n_steps,
+            rows_per_launch, lg.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        _check(rc, "decode_tokens failed")
+        return lg
 
 
 class Stream:

@@ -509,6 +509,33 @@ int32_t moonshine_b200_decode_with_drafts(int32_t transcriber_handle, const floa
   return MOONSHINE_ERROR_NONE;
 }
 
+int32_t moonshine_b200_decode_tokens(int32_t transcriber_handle, const float* const* audio, const uint64_t* lengths,
+                                     uint64_t count, const int32_t* tokens, int32_t tokens_stride, int32_t n_steps,
+                                     int32_t rows_per_launch, float* logits_out) {
+  CHECK_HANDLE(t, transcriber_handle);
+  if (t->model() == nullptr || audio == nullptr || lengths == nullptr || tokens == nullptr || logits_out == nullptr ||
+      n_steps <= 0 || tokens_stride < n_steps || rows_per_launch < 2 || rows_per_launch > 16)
+    return MOONSHINE_ERROR_INVALID_ARGUMENT;
+  try {
+    std::lock_guard<std::mutex> lock(t->model_mutex());
+    DebugCapture dbg;
+    std::vector<float> lg;
+    dbg.logits = &lg;
+    dbg.logits_steps = n_steps;
+    dbg.forced = tokens;
+    dbg.forced_stride = tokens_stride;
+    dbg.rows_per_launch = rows_per_launch;
+    std::vector<std::vector<int32_t>> ids;
+    t->model()->transcribe(audio, lengths, (int)count, t->options().max_tokens_per_second, ids, &dbg);
+    std::memset(logits_out, 0, (size_t)n_steps * count * t->model()->dims().vocab * sizeof(float));
+    std::memcpy(logits_out, lg.data(), std::min(lg.size(), (size_t)n_steps * count * t->model()->dims().vocab) * sizeof(float));
+  } catch (const std::exception& e) {
+    MSB_LOGF("decode_tokens failed: %s", e.what());
+    return MOONSHINE_ERROR_UNKNOWN;
+  }
+  return MOONSHINE_ERROR_NONE;
+}
+
 // ---- host-only parity hooks (no GPU needed): the product's own helpers, callable from the CPU tests that
 // compare them with a build of the reference's own sources ----
 int64_t moonshine_b200_debug_tokens_to_text(const uint8_t* tokenizer, uint64_t tokenizer_size, const int32_t* ids,

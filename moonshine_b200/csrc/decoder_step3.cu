@@ -1809,7 +1809,25 @@ __global__ void decoder_verify_plan_kernel(const __grid_constant__ DecoderParams
   if (threadIdx.x == 0) *p.n_active = alive;
 }
 
+// Splice from explicit rows back into the lockstep loop: the argmax candidates of "step - 1" are seeded so that the next
+// lockstep launch resolves utterance b's previous id to cur[b] (lowest index wins among equal values, every other chunk
+// carries -inf).
+__global__ void decoder_seed_candidates_kernel(const __grid_constant__ DecoderParams p, const int* cur, int parity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_vchunk * p.B) return;
+  const int c = i / p.B, b = i - c * p.B;
+  float* cv = p.cand_val + (int64_t)parity * p.n_vchunk * p.B;
+  int* ci = p.cand_idx + (int64_t)parity * p.n_vchunk * p.B;
+  cv[i] = c == 0 ? 0.f : -INFINITY;
+  ci[i] = c == 0 ? cur[b] : 0x7fffffff;
+}
+
 }  // namespace
+
+void launch_decoder_seed_candidates(const DecoderParams& p, const int* cur, int parity, cudaStream_t stream) {
+  const int n = p.n_vchunk * p.B;
+  decoder_seed_candidates_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, cur, parity);
+}
 
 void launch_decoder_verify_plan(const DecoderParams& p, const VerifyState& s, int k, int n, int bos, int eos, cudaStream_t stream) {
   if (n < 1 || n > 16) throw std::runtime_error("decoder v3: 1..16 rows per utterance");

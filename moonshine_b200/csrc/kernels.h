@@ -245,6 +245,8 @@ struct VerifyState {
   int draft_stride;
 };
 // books launch k-1 and writes the rows of launch k (p: explicit-row parameters, p.B = B_utt * n rows)
+// seeds the argmax candidates of parity `parity` so that the lockstep kernels resolve utterance b's previous id to cur[b]
+void launch_decoder_seed_candidates(const DecoderParams& p, const int* cur, int parity, cudaStream_t stream);
 void launch_decoder_verify_plan(const DecoderParams& p, const VerifyState& s, int k, int n, int bos, int eos, cudaStream_t stream);
 size_t decoder_step3_smem_bytes(const DecoderParams& p);
 // fills nb_self / nb_cross / nx / job_first / job_ncta for batch size p.B on a grid of `grid` CTAs

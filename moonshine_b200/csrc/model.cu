@@ -551,8 +551,8 @@ void Model::build_weights(const WeightFile& wf) {
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
   dec_.c4_cs = c4_cs_; dec_.c4_nc = c4_nc_;
   {
-    const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob (bit mask, see DecoderParams::pf_mask); off by default: measured neutral or slightly negative at tiny/32 and base/256 (profiles/r2e_prefetch_ab.txt)
-    dec_.pf_mask = e ? std::atoi(e) : 0;
+    const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob (bit mask, see DecoderParams::pf_mask); default 32 = evict-first hint on v3's cross K/V stream (base/256 1677 -> 1582 us/step, base-streaming/64 842 -> 776); the prefetch bits measured neutral or negative (profiles/r2e_prefetch_ab.txt)
+    dec_.pf_mask = e ? std::atoi(e) : 32;
   }
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
@@ -1154,22 +1154,9 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   }
   std::vector<std::vector<int32_t>> hooked_tokens;  // filled by the host-stepped loop
   int steps_launched = max_steps;
-  bool any_draft = false;
-  const int* const* drafts = (plan && plan->draft && plan->draft_len) ? plan->draft : dbg_draft_;
-  const int* draft_lens = (plan && plan->draft && plan->draft_len) ? plan->draft_len : dbg_draft_len_;
-  dbg_draft_ = nullptr;
-  dbg_draft_len_ = nullptr;
-  if (drafts && draft_lens)
-    for (int b = 0; b < B; b++) any_draft |= drafts[b] != nullptr && draft_lens[b] > 0;
-  const bool verify = any_draft && hook == nullptr && xattn == nullptr && dbg == nullptr && use_v3 && max_steps > 0 &&
-                      B * kVerifyRows <= 4096;
-  if (verify) {
-    // ---- verify-then-continue on explicit rows (decode_full, moonshine-streaming-model.cpp:1192-1397) ----
-    // kVerifyRows consecutive draft positions of every utterance per launch; the plan kernel between two launches books
-    // the emitted ids and moves each utterance on (verify -> auto-regressive -> done).  An accepted draft of m ids
-    // costs ceil((m + 1) / kVerifyRows) launches instead of m + 1.
-    const int n = kVerifyRows, R = B * n;
-    DecoderParams q = p;
+  // explicit rows: every per-row buffer grows to R rows (the caches stay per utterance)
+  auto widen = [&](DecoderParams& q, int n) {
+    const int R = B * n;
     q.B = R; q.B_utt = B; q.row_group = n;
     hbuf_.reserve((size_t)2 * R * D);
     part_.reserve((size_t)std::max(2 * H + q.n_chunk, H + q.ffn_ksplit + 1) * R * D);
@@ -1179,13 +1166,70 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     cand_val_.reserve((size_t)2 * q.n_vchunk * R);
     cand_idx_.reserve((size_t)2 * q.n_vchunk * R);
     rows_dev_.reserve((size_t)4 * R);
-    vstate_dev_.reserve((size_t)4 * B);
-    const int dstride = Smax + 1;
-    draft_dev_.reserve((size_t)B * dstride + B);
     q.hbuf = hbuf_.ptr; q.part = part_.ptr; q.attc = attc_.ptr; q.act = act_.ptr; q.xfin = xfin_.ptr;
     q.cand_val = cand_val_.ptr; q.cand_idx = cand_idx_.ptr;
     q.row_tok = rows_dev_.ptr; q.row_pos = rows_dev_.ptr + R; q.row_nin = rows_dev_.ptr + 2 * R; q.row_utt = rows_dev_.ptr + 3 * R;
     q.logits_out = nullptr; q.xattn_out = nullptr; q.forced = nullptr; q.prof = nullptr;
+    decoder_step3_plan(q, grid);
+    return R;
+  };
+  const bool multi = dbg && dbg->forced && dbg->rows_per_launch > 1 && use_v3 && hook == nullptr && xattn == nullptr && max_steps > 0;
+  bool any_draft = false;
+  const int* const* drafts = (plan && plan->draft && plan->draft_len) ? plan->draft : dbg_draft_;
+  const int* draft_lens = (plan && plan->draft && plan->draft_len) ? plan->draft_len : dbg_draft_len_;
+  dbg_draft_ = nullptr;
+  dbg_draft_len_ = nullptr;
+  if (drafts && draft_lens)
+    for (int b = 0; b < B; b++) any_draft |= drafts[b] != nullptr && draft_lens[b] > 0;
+  const bool verify = any_draft && hook == nullptr && xattn == nullptr && dbg == nullptr && use_v3 && max_steps > 0 &&
+                      B * kVerifyRows <= 4096;
+  bool spliced = false;  // verify finished in the lockstep loop (which needs its finalize launch)
+  if (multi) {
+    // ---- teacher-forced multi-token decoder runs (decode_tokens, moonshine-streaming-model.cpp:1136-1190): n consecutive
+    // positions of every utterance per launch, row i attending the cache and rows 0..i of its own launch; logits of
+    // every position come back in the [steps][B][V] layout of the single-token dump ----
+    int n = 2;
+    while (n < dbg->rows_per_launch && n < 16) n *= 2;
+    DecoderParams q = p;
+    const int R = widen(q, n);
+    logits_rows_.reserve((size_t)R * V);
+    q.logits_out = logits_rows_.ptr;
+    std::vector<int> rows((size_t)4 * R);
+    int k = 0;
+    for (int t0 = 0; t0 < max_steps; t0 += n, k++) {
+      for (int b = 0; b < B; b++)
+        for (int i = 0; i < n; i++) {
+          const int r = b * n + i, t = t0 + i;
+          const bool on = t < mlen[b] && t < dbg->forced_stride;
+          rows[r] = on ? dbg->forced[(size_t)b * dbg->forced_stride + t] : -1;
+          rows[(size_t)R + r] = on ? t : 0;
+          rows[(size_t)2 * R + r] = on ? i : 0;
+          rows[(size_t)3 * R + r] = b;
+        }
+      CUDA_CHECK(cudaMemcpyAsync(rows_dev_.ptr, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      q.step = k;
+      launch_decoder_step3(q, grid, stream_);
+      for (int b = 0; b < B; b++)
+        for (int i = 0; i < n; i++) {
+          const int t = t0 + i;
+          if (t < dbg_steps && rows[(size_t)b * n + i] >= 0)
+            CUDA_CHECK(cudaMemcpyAsync(logits_dbg_.ptr + ((size_t)t * B + b) * V, logits_rows_.ptr + (size_t)(b * n + i) * V,
+                                       (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+        }
+      CUDA_CHECK(cudaStreamSynchronize(stream_));  // `rows` is reused by the next launch
+    }
+    steps_launched = k;
+  } else if (verify) {
+    // ---- verify-then-continue on explicit rows (decode_full, moonshine-streaming-model.cpp:1192-1397) ----
+    // kVerifyRows consecutive draft positions of every utterance per launch; the plan kernel between two launches books
+    // the emitted ids and moves each utterance on (verify -> auto-regressive -> done).  An accepted draft of m ids
+    // costs ceil((m + 1) / kVerifyRows) launches instead of m + 1.
+    const int n = kVerifyRows;
+    DecoderParams q = p;
+    widen(q, n);
+    vstate_dev_.reserve((size_t)4 * B);
+    const int dstride = Smax + 1;
+    draft_dev_.reserve((size_t)B * dstride + B);
     std::vector<int> hd_((size_t)B * dstride + B, 0);
     int m_max = 0;
     for (int b = 0; b < B; b++) {
@@ -1199,7 +1243,6 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     VerifyState st;
     st.mode = vstate_dev_.ptr; st.pos = vstate_dev_.ptr + B; st.cur = vstate_dev_.ptr + 2 * B; st.prev_n = vstate_dev_.ptr + 3 * B;
     st.draft = draft_dev_.ptr; st.draft_len = draft_dev_.ptr + (size_t)B * dstride; st.draft_stride = dstride;
-    decoder_step3_plan(q, grid);
     int k = 0;
     auto run_steps = [&](int count) {
       for (int i = 0; i < count; i++, k++) {
@@ -1216,10 +1259,35 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       CUDA_CHECK(cudaMemcpyAsync(hn, ntok_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));
       CUDA_CHECK(cudaMemcpyAsync(hn + B, vstate_dev_.ptr, B * sizeof(int), cudaMemcpyDeviceToHost, stream_));  // modes
       CUDA_CHECK(cudaStreamSynchronize(stream_));
-      int rem = 0;
+      int rem = 0, pos_lo = 1 << 30, pos_hi = -1;
+      bool all_ar = true;
       for (int b = 0; b < B; b++)
-        if (hn[B + b] != 2) rem = std::max(rem, mlen[b] - (hn[b] - 1));
+        if (hn[B + b] != 2) {
+          rem = std::max(rem, mlen[b] - (hn[b] - 1));
+          pos_lo = std::min(pos_lo, hn[b] - 1);
+          pos_hi = std::max(pos_hi, hn[b] - 1);
+          all_ar &= hn[B + b] == 1;
+        }
       if (rem <= 0) break;
+      if (all_ar && pos_lo == pos_hi && pos_lo >= 1) {
+        // Every live utterance waits at the same position (always so for a single stream): the tail is the ordinary
+        // lockstep loop on the kernel that is fastest for this batch (cluster-resident layers for small ones).  The
+        // caches are position-indexed and shared by both row models; only the "previous id" hand-over is seeded.
+        p.hbuf = hbuf_.ptr; p.part = part_.ptr; p.attc = attc_.ptr; p.act = act_.ptr; p.xfin = xfin_.ptr;
+        p.cand_val = cand_val_.ptr; p.cand_idx = cand_idx_.ptr;
+        // the phase counters are cumulative per launch shape ((epoch + 1) * jobs): a new shape starts a new epoch count
+        CUDA_CHECK(cudaMemsetAsync(sync3_.ptr, 0, sizeof(unsigned), stream_));
+        CUDA_CHECK(cudaMemsetAsync(sync3_.ptr + 32, 0, (kSync3Words - 32) * sizeof(unsigned), stream_));
+        launch_decoder_seed_candidates(p, st.cur, (pos_lo - 1) & 1, stream_);
+        for (int t = pos_lo; t < max_steps; t++, k++) {
+          p.step = t;
+          p.prof = nullptr;
+          p.logits_out = nullptr;
+          launch_step();
+        }
+        spliced = true;
+        break;
+      }
       run_steps(std::min(rem, 16));  // bounded bursts: an EOS ends the tail early, the next read sees it
     }
     steps_launched = k;
@@ -1362,7 +1430,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       fprintf(stderr, "\n");
     }
   }
-  if (!verify) {
+  if ((!verify || spliced) && !multi) {
     p.step = max_steps;
     launch_decoder_finalize(p, stream_);
     stage("decoder_finalize", -1, 32);

@@ -25,6 +25,8 @@ struct DebugCapture {
   const int32_t* forced = nullptr;               // [B][forced_stride] teacher-forced ids (incl. start)
   int forced_stride = 0;
   bool skip_decode = false;
+  int rows_per_launch = 0;                       // > 1 with `forced`: teacher-forced MULTI-token decoder runs (decode_tokens,
+                                                 // moonshine-streaming-model.cpp:1136-1190): this many positions per launch
 };
 
 // Streaming architectures: what the host bookkeeping (Transcriber, mirroring
@@ -174,6 +176,7 @@ class Model {
   PinnedBuffer<float> pin_bias_f32_;
   DeviceBuffer<int> nactive_;
   DeviceBuffer<int> rows_dev_, vstate_dev_, draft_dev_;  // explicit-row decoding (speculative verify)
+  DeviceBuffer<float> logits_rows_;                      // [rows][V] logits of one explicit-row launch (decode_tokens)
   const int* const* dbg_draft_ = nullptr;                // drafts for the NEXT run() when its plan carries none (test entry)
   const int* dbg_draft_len_ = nullptr;
   PinnedBuffer<int> pin_i32_;

@@ -89,3 +89,35 @@ def test_streaming_updates_with_and_without_draft_verification_print_the_same_li
     assert texts["1"] == texts["0"]
     assert any(any(x) for x in texts["1"])
     assert sum(steps["1"][1:]) < sum(steps["0"][1:]), (steps["1"], steps["0"])
+
+
+@pytest.mark.parametrize("arch,rows", [("test_streaming", 8), ("test", 4), ("tiny_streaming", 16)])
+def test_multi_token_runs_give_the_single_token_logits(arch, rows):
+    """decode_tokens (n > 1): the logits of positions run `rows` at a time must be those of the one-position-per-launch
+    teacher-forced loop (the path pinned against the oracle in test_parity_gpu / test_streaming_gpu) and of the oracle."""
+    from tests.test_streaming_gpu import soracle
+    from tests.util import oracle_for
+    d = ARCHS[arch]
+    audios = [synth_audio(i, n) for i, n in enumerate([48000, 33000, 64000])]
+    t = make(arch)
+    ids = greedy(t, arch, audios)
+    steps = max(len(x) for x in ids) - 1
+    forced = np.zeros((len(audios), steps + 2), np.int32)
+    for i, x in enumerate(ids):
+        forced[i, :len(x)] = x
+    _, single, _ = t.debug_run(audios, d.dim, d.vocab, forced=forced, logits_steps=steps, want_encoder=False, max_tokens=300)
+    multi = t.decode_tokens(audios, forced, d.vocab, steps, rows_per_launch=rows)
+    for i, x in enumerate(ids):
+        for s in range(len(x) - 1):
+            ref = single[s, i]
+            assert np.abs(multi[s, i] - ref).max() <= 2e-5 * np.abs(ref).max(), (i, s)
+    # and against the oracle directly (utterance 0)
+    if ARCHS[arch].streaming:
+        toks, ref_logits, _ = soracle(arch).transcribe_segment(audios[0], is_final=True)
+    else:
+        toks, ref_logits, _ = oracle_for(arch, 0, "scaled").greedy(audios[0])
+    for s in range(min(len(toks) - 1, steps)):
+        if toks[:s + 1] != ids[0][:s + 1]:
+            break
+        assert np.abs(multi[s, 0] - ref_logits[s]).max() < 1e-3 * np.abs(ref_logits[s]).max(), s
+    t.close()
