@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmoonshine.so")
 
 SOURCES = [
-    "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "ring_bench.cu", "kernels_misc.cu", "decoder_step.cu", "decoder_step2.cu", "decoder_step3.cu", "decoder_step4.cu", "model.cu",
+    "gemm_simt.cu", "gemm_tc.cu", "gemm_planes.cu", "attention_tc.cu", "ring_bench.cu", "kernels_misc.cu", "decoder_step.cu", "decoder_step2.cu", "decoder_step3.cu", "decoder_step4.cu", "model.cu",
     "weights.cpp", "tokenizer.cpp", "word_alignment.cpp", "transcriber.cpp", "c_api.cpp",
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -687,7 +687,39 @@ int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, in
     GemmParams g;
     g.A = dA; g.W = dW; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.rs = ldc;
     g.bias = d_bias; g.act = act; g.accumulate = accumulate;
-    if (impl == 1) launch_gemm_simt(g, nullptr);
+    if (impl == 3 || impl == 4) {
+      // plane-fed kernel: both operands are converted to hi/lo plane tiles on the device first.  impl 4 also makes the
+      // epilogue write the result as plane tiles and reads those back through a second plane-fed product with I_N.
+      DeviceBuffer<float> pa, pw, pc;
+      pa.reserve(plane_tiles_bytes(M, K) / 4);
+      pw.reserve(plane_tiles_bytes(N, K) / 4);
+      launch_rows_to_planes(dA, lda, M, K, reinterpret_cast<unsigned char*>(pa.ptr), nullptr);
+      CUDA_CHECK(cudaMemsetAsync(pw.ptr, 0, pw.bytes(), nullptr));
+      launch_rows_to_planes(dW, ldw, N, K, reinterpret_cast<unsigned char*>(pw.ptr), nullptr);
+      GemmPlanesParams q;
+      q.A = reinterpret_cast<unsigned char*>(pa.ptr); q.W = reinterpret_cast<unsigned char*>(pw.ptr);
+      q.M = M; q.N = N; q.K = K; q.C = dC; q.ldc = ldc; q.bias = d_bias; q.act = act; q.accumulate = accumulate;
+      if (impl == 4) {
+        pc.reserve(plane_tiles_bytes(M, N) / 4);
+        q.P = reinterpret_cast<unsigned char*>(pc.ptr);
+      }
+      launch_gemm_planes(q, nullptr);
+      if (impl == 4) {  // dC <- (planes of C) x I_N
+        DeviceBuffer<float> eye, pe;
+        eye.reserve((size_t)N * N);
+        CUDA_CHECK(cudaMemsetAsync(eye.ptr, 0, eye.bytes(), nullptr));
+        std::vector<float> h((size_t)N * N, 0.f);
+        for (int i = 0; i < N; i++) h[(size_t)i * N + i] = 1.0f;
+        CUDA_CHECK(cudaMemcpy(eye.ptr, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        pe.reserve(plane_tiles_bytes(N, N) / 4);
+        CUDA_CHECK(cudaMemsetAsync(pe.ptr, 0, pe.bytes(), nullptr));
+        launch_rows_to_planes(eye.ptr, N, N, N, reinterpret_cast<unsigned char*>(pe.ptr), nullptr);
+        GemmPlanesParams r;
+        r.A = q.P; r.W = reinterpret_cast<unsigned char*>(pe.ptr); r.M = M; r.N = N; r.K = N; r.C = dC; r.ldc = ldc;
+        launch_gemm_planes(r, nullptr);
+      }
+      CUDA_CHECK(cudaDeviceSynchronize());
+    } else if (impl == 1) launch_gemm_simt(g, nullptr);
     else if (impl == 2) launch_gemm_tc(g, nullptr);
     else launch_gemm(g, nullptr);
     CUDA_CHECK(cudaGetLastError());

@@ -55,6 +55,47 @@ void launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
 void launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
+// Plane-fed GEMM (gemm_planes.cu): both operands pre-split to bf16 hi/lo planes in UMMA tile order, fed by bulk copies.
+// Plane layout of an [R][K] operand (K % 32 == 0): tile (rt = r / 128, kb = k / 32) at ((rt * K/32) + kb) * kPlaneTileBytes,
+// [hi 128 rows x 64 B | lo 128 rows x 64 B], chunk c of row r at position c ^ ((r >> 1) & 3).  Rows beyond R are padding
+// (weights: zeros written at load; activations: whatever is there -- they only reach output rows that are never stored).
+// ---------------------------------------------------------------------------
+constexpr int kPlaneTileBytes = 16384;
+inline size_t plane_tiles_bytes(int64_t rows, int K) { return (size_t)((rows + 127) / 128) * (size_t)(K / 32) * kPlaneTileBytes; }
+struct GemmPlanesParams {
+  const unsigned char* A = nullptr;  // planes of the activations [M][K]
+  const unsigned char* W = nullptr;  // planes of the weights [N][K]
+  int M = 0, N = 0, K = 0;
+  float* C = nullptr;                // fp32 output rows (row stride ldc), may be null when only planes are wanted
+  int64_t ldc = 0;
+  unsigned char* P = nullptr;        // optional: the output as planes of an [M][N] operand (input of the next GEMM)
+  int p_taps = 1, p_stride = 1;      // > 1 taps: P is the im2col operand of a following convolution (row r = p_taps output rows from p_stride * r)
+  const float* bias = nullptr;       // [N]
+  int act = 0;                       // 1 = exact-erf GELU
+  int accumulate = 0;                // C += result
+  const int* pos = nullptr;          // interleaved-pair RoPE on columns n < rope_cols (per-row position), like GemmParams
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_cols = 0, head_dim = 1, rot_dim = 0;
+  // optional column split: columns n >= n_split (a multiple of 32) are stored TRANSPOSED instead, Vt[vt_row[m] + (n - n_split) * vt_ld]
+  // (rows with vt_row[m] < 0 are skipped) -- the encoder's V^T_b[e][t] next to its Q | K rows
+  int n_split = 0;
+  float* Vt = nullptr;
+  const int64_t* vt_row = nullptr;
+  int64_t vt_ld = 0;
+};
+bool gemm_planes_supported(const GemmPlanesParams& p);
+void launch_gemm_planes(const GemmPlanesParams& p, cudaStream_t stream);
+// y (optional fp32 rows) and planes of LayerNorm(x) * gamma
+void launch_layernorm_planes(const float* x, float* y, unsigned char* planes, const float* gamma, int64_t rows, int D,
+                             cudaStream_t stream);
+// GroupNorm apply of the conv1 rows written as the plane tiles of conv2's im2col operand [tot1 / 3][7 * D]
+void launch_groupnorm_im2col_planes(const float* h1, const int* t1, const int64_t* off1, const double* gn_partial, int nblk,
+                                    const float* gamma, const float* beta, int D, int B, int max_t1, unsigned char* planes,
+                                    cudaStream_t stream);
+void launch_rows_to_planes(const float* src, int64_t ld, int64_t rows, int K, unsigned char* planes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
 // Frontend
 // ---------------------------------------------------------------------------
 // conv1 (1 -> D, k=127, s=64, no bias) + tanh, channel-last output rows

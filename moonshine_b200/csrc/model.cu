@@ -73,6 +73,32 @@ size_t pack_planes(BlobBuilder& bb, int N, int K, Get get) {
   return off;
 }
 
+// W[n][k] as full 128-row plane tiles (gemm_planes.cu: tile (n / 128, k / 32) = [hi 8 KB | lo 8 KB], zero-padded rows)
+template <typename Get>
+size_t pack_tile_planes(BlobBuilder& bb, int N, int K, Get get) {
+  const size_t bytes = plane_tiles_bytes(N, K);
+  const size_t off = bb.add(bytes / 4);
+  uint16_t* P = reinterpret_cast<uint16_t*>(&bb.data[off]);
+  std::memset(P, 0, bytes);
+  const int nkb = K / 32;
+  for (int n = 0; n < N; n++) {
+    const int r = n & 127;
+    for (int kb = 0; kb < nkb; kb++) {
+      uint16_t* hi = P + ((size_t)(n >> 7) * nkb + kb) * (kPlaneTileBytes / 2);
+      uint16_t* lo = hi + kPlaneTileBytes / 4;
+      for (int kk = 0; kk < 32; kk++) {
+        const float x = get(n, kb * 32 + kk);
+        const uint16_t h = bf16_round(x);
+        const uint16_t l = bf16_round(x - bf16_value(h));
+        const size_t at = (size_t)r * 32 + (size_t)(((kk >> 3) ^ ((r >> 1) & 3)) * 8 + (kk & 7));
+        hi[at] = h;
+        lo[at] = l;
+      }
+    }
+  }
+  return off;
+}
+
 }  // namespace
 
 int Model::max_len_for(uint64_t n_samples, float max_tokens_per_second) {
@@ -165,6 +191,7 @@ Model::Model(const Model& src, int device) : d_(src.d_), device_(device) {
   };
   w1t_ = rb(src.w1t_); gn_w_ = rb(src.gn_w_); gn_b_ = rb(src.gn_b_);
   conv2_w_ = rb(src.conv2_w_); conv2_b_ = rb(src.conv2_b_); conv3_w_ = rb(src.conv3_w_); conv3_b_ = rb(src.conv3_b_);
+  conv2P_ = rbb(src.conv2P_); conv3P_ = rbb(src.conv3P_);
   enc_final_ln_ = rb(src.enc_final_ln_);
   s_lin_w_ = rb(src.s_lin_w_); s_c1_w_ = rb(src.s_c1_w_); s_c1_b_ = rb(src.s_c1_b_); s_c2_w_ = rb(src.s_c2_w_); s_c2_b_ = rb(src.s_c2_b_);
   pos_emb_ = rb(src.pos_emb_); proj_w_ = rb(src.proj_w_);
@@ -173,7 +200,9 @@ Model::Model(const Model& src, int device) : d_(src.d_), device_(device) {
   for (EncLayer& e : enc_) {
     e.ln1 = rb(e.ln1); e.wqk = rb(e.wqk); e.wv = rb(e.wv); e.wo = rb(e.wo); e.ln2 = rb(e.ln2);
     e.w1 = rb(e.w1); e.b1 = rb(e.b1); e.w2 = rb(e.w2); e.b2 = rb(e.b2);
+    e.wqkP = rbb(e.wqkP); e.woP = rbb(e.woP); e.w1P = rbb(e.w1P); e.w2P = rbb(e.w2P);
   }
+  enc_planes_ = src.enc_planes_;
   dec_ = src.dec_;
   dec_.embed = rb(src.dec_.embed); dec_.embT = rb(src.dec_.embT); dec_.final_ln = rb(src.dec_.final_ln);
   dec_.embP = rbb(reinterpret_cast<const unsigned char*>(src.dec_.embP));
@@ -214,9 +243,9 @@ void Model::build_weights(const WeightFile& wf) {
   const int E = d_.streaming ? d_.enc_dim : D;      // encoder hidden size
   const int EI = d_.streaming ? d_.enc_ffn : I;
   if (E % 4 || EI % 4 || E % H || (E / H) % 4) throw std::runtime_error("encoder dims must be multiples of 4");
-  size_t o_w1t = 0, o_gnw = 0, o_gnb = 0, o_c2 = 0, o_c2b = 0, o_c3 = 0, o_c3b = 0, o_encln = 0;
+  size_t o_w1t = 0, o_gnw = 0, o_gnb = 0, o_c2 = 0, o_c2b = 0, o_c3 = 0, o_c3b = 0, o_encln = 0, o_conv2P = 0, o_conv3P = 0;
   size_t o_slin = 0, o_sc1 = 0, o_sc1b = 0, o_sc2 = 0, o_sc2b = 0, o_pos = 0, o_proj = 0;
-  struct EncOff { size_t ln1, wqk, wv, wo, ln2, w1, b1, w2, b2; };
+  struct EncOff { size_t ln1, wqk, wv, wo, ln2, w1, b1, w2, b2, wqkP = 0, woP = 0, w1P = 0, w2P = 0; };
   std::vector<EncOff> eo(d_.enc_layers);
   if (!d_.streaming) {
   // conv1 [D][1][127] -> [127][D]
@@ -307,6 +336,31 @@ void Model::build_weights(const WeightFile& wf) {
     // adapter (lora/export.py:130-144): position table + optional projection E -> D
     o_pos = bb.add_copy(wf.get("model.decoder.pos_emb.weight", {d_.max_pos_emb, E}).data, (size_t)d_.max_pos_emb * E);
     if (E != D) o_proj = bb.add_copy(wf.get("model.decoder.proj.weight", {D, E}).data, (size_t)D * E);
+  }
+
+  // Encoder dense weights once more as bf16 hi/lo plane tiles: the plane-fed tcgen05 GEMM (gemm_planes.cu) streams them
+  // with bulk copies, MMA-ready (same bytes as the fp32 copy, which the unfused / odd-shape paths keep using).
+  {
+    const int Ee = d_.streaming ? d_.enc_dim : D, EIe = d_.streaming ? d_.enc_ffn : I;
+    enc_planes_ = Ee % 32 == 0 && EIe % 32 == 0 && Ee <= 512;
+    if (const char* e = std::getenv("MOONSHINE_B200_ENC")) enc_planes_ = enc_planes_ && std::string(e) != "classic";
+    if (enc_planes_ && !d_.streaming) {  // conv2 [2D][7D] and conv3 [D][6D] (tap-major K, as the fp32 copies)
+      const size_t c2 = o_c2, c3 = o_c3;
+      o_conv2P = pack_tile_planes(bb, 2 * D, 7 * D, [&](int n, int k) { return bb.data[c2 + (size_t)n * 7 * D + k]; });
+      o_conv3P = pack_tile_planes(bb, D, 6 * D, [&](int n, int k) { return bb.data[c3 + (size_t)n * 6 * D + k]; });
+    }
+    if (enc_planes_) {
+      for (int l = 0; l < d_.enc_layers; l++) {
+        const size_t wqk = eo[l].wqk, wo = eo[l].wo, w1 = eo[l].w1, w2 = eo[l].w2;
+        const size_t wv = eo[l].wv;  // q | k | v rows in one block: one GEMM makes all three
+        eo[l].wqkP = pack_tile_planes(bb, 3 * Ee, Ee, [&](int n, int k) {
+          return n < 2 * Ee ? bb.data[wqk + (size_t)n * Ee + k] : bb.data[wv + (size_t)(n - 2 * Ee) * Ee + k];
+        });
+        eo[l].woP = pack_tile_planes(bb, Ee, Ee, [&](int n, int k) { return bb.data[wo + (size_t)n * Ee + k]; });
+        eo[l].w1P = pack_tile_planes(bb, EIe, Ee, [&](int n, int k) { return bb.data[w1 + (size_t)n * Ee + k]; });
+        eo[l].w2P = pack_tile_planes(bb, Ee, EIe, [&](int n, int k) { return bb.data[w2 + (size_t)n * EIe + k]; });
+      }
+    }
   }
 
   // ---- decoder ----
@@ -532,6 +586,10 @@ void Model::build_weights(const WeightFile& wf) {
   if (!d_.streaming) {
     w1t_ = base + o_w1t; gn_w_ = base + o_gnw; gn_b_ = base + o_gnb;
     conv2_w_ = base + o_c2; conv2_b_ = base + o_c2b; conv3_w_ = base + o_c3; conv3_b_ = base + o_c3b;
+    if (enc_planes_) {
+      conv2P_ = reinterpret_cast<const unsigned char*>(base) + o_conv2P * 4;
+      conv3P_ = reinterpret_cast<const unsigned char*>(base) + o_conv3P * 4;
+    }
   } else {
     s_lin_w_ = base + o_slin; s_c1_w_ = base + o_sc1; s_c1_b_ = base + o_sc1b;
     s_c2_w_ = base + o_sc2; s_c2_b_ = base + o_sc2b;
@@ -541,7 +599,12 @@ void Model::build_weights(const WeightFile& wf) {
   enc_.resize(d_.enc_layers);
   for (int l = 0; l < d_.enc_layers; l++) {
     enc_[l] = {base + eo[l].ln1, base + eo[l].wqk, base + eo[l].wv, base + eo[l].wo, base + eo[l].ln2,
-               base + eo[l].w1, base + eo[l].b1, base + eo[l].w2, base + eo[l].b2};
+               base + eo[l].w1, base + eo[l].b1, base + eo[l].w2, base + eo[l].b2, nullptr, nullptr, nullptr, nullptr};
+    if (enc_planes_) {
+      const unsigned char* bytes = reinterpret_cast<const unsigned char*>(base);
+      enc_[l].wqkP = bytes + eo[l].wqkP * 4; enc_[l].woP = bytes + eo[l].woP * 4;
+      enc_[l].w1P = bytes + eo[l].w1P * 4; enc_[l].w2P = bytes + eo[l].w2P * 4;
+    }
   }
   enc_final_ln_ = base + o_encln;
   wk_all_ = base + o_wk_all;
@@ -771,7 +834,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   // int64: off1[B] offQ[BH] offK[BH] offS[BH] offVh[BH] offO[BH] offXb[B] offVt[B] offKc[B] offVc[B]
   //        offMem[B] frRow[B] c1A[B] c1C[B] c2A[B] c2C[B]
   const size_t n_i32 = (size_t)4 * B + tot3 + BH + B + 3 * B;
-  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B + 6 * B;
+  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B + 6 * B + (size_t)tot3;  // + vtRow[tot3]: V^T address of every packed row (-1: padding row)
   pin_i32_.reserve(n_i32);
   pin_i64_.reserve(n_i64);
   meta_i32_.reserve(n_i32);
@@ -788,13 +851,18 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
           *h_offvt = h_offxb + B, *h_offkc = h_offvt + B, *h_offvc = h_offkc + B;
   int64_t *h_offmem = h_offvc + B, *h_frrow = h_offmem + B, *h_c1a = h_frrow + B, *h_c1c = h_c1a + B,
           *h_c2a = h_c1c + B, *h_c2c = h_c2a + B;
+  int64_t* h_vtrow = h_c2c + B;
+  for (int64_t r = 0; r < tot3; r++) h_vtrow[r] = -1;
   std::memset(h_pos, 0, sizeof(int) * tot3);
   for (int b = 0; b < B; b++) {
     h_ns[b] = nsamp[b]; h_t1[b] = T1[b]; h_t3[b] = T3[b]; h_ml[b] = mlen[b];
     h_tm[b] = Tm[b]; h_fn[b] = Fn[b]; h_c1[b] = C1[b];
     h_off1[b] = off1[b];
     const int64_t r3 = r3v[b];
-    for (int t = 0; t < T3[b]; t++) h_pos[r3 + t] = t;
+    for (int t = 0; t < T3[b]; t++) {
+      h_pos[r3 + t] = t;
+      h_vtrow[r3 + t] = (int64_t)b * E * Tp + t;
+    }
     h_dzb[b] = E;
     h_offxb[b] = r3 * E;
     h_offmem[b] = r3 * D;
@@ -828,6 +896,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
                 *d_offvt = d_offxb + B, *d_offkc = d_offvt + B, *d_offvc = d_offkc + B;
   const int64_t *d_offmem = d_offvc + B, *d_frrow = d_offmem + B, *d_c1a = d_frrow + B, *d_c1c = d_c1a + B,
                 *d_c2a = d_c1c + B, *d_c2c = d_c2a + B;
+  const int64_t* d_vtrow = d_c2c + B;
 
   // ---------------- workspaces ----------------
   auto reserve_zero = [&](DeviceBuffer<float>& buf, size_t n) {
@@ -836,9 +905,15 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       CUDA_CHECK(cudaMemsetAsync(buf.ptr, 0, buf.bytes(), stream_));
     }
   };
+  const bool conv_planes = !S && enc_planes_ && conv2P_ != nullptr;
   if (!S) {
     reserve_zero(h1_, (size_t)(tot1 + 8) * D);
-    reserve_zero(h2_, (size_t)(tot2 + 4) * 2 * D);
+    if (conv_planes) {  // im2col operands of conv2 / conv3 as plane tiles (written by GroupNorm-apply / conv2's epilogue)
+      reserve_zero(a2P_, plane_tiles_bytes(tot2, 7 * D) / 4);
+      reserve_zero(a3P_, plane_tiles_bytes(tot3, 6 * D) / 4);
+    } else {
+      reserve_zero(h2_, (size_t)(tot2 + 4) * 2 * D);
+    }
   } else {
     reserve_zero(frames_, (size_t)(tot_h + 8) * 80);
     reserve_zero(h1_, (size_t)(tot_h + 8) * E);
@@ -859,7 +934,13 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     if (need_scores) reserve_zero(scores_, (size_t)BH * maxT3 * Tp);
   }
   reserve_zero(attn_, (size_t)tot3 * E);
-  reserve_zero(mid_, (size_t)tot3 * EI);
+  if (enc_planes_) {  // activations as bf16 hi/lo plane tiles (same bytes as fp32 rows, rounded up to 128-row tiles)
+    reserve_zero(lnP_, plane_tiles_bytes(tot3, E) / 4);
+    reserve_zero(attnP_, plane_tiles_bytes(tot3, E) / 4);
+    reserve_zero(midP_, plane_tiles_bytes(tot3, EI) / 4);
+  } else {
+    reserve_zero(mid_, (size_t)tot3 * EI);
+  }
   reserve_zero(enc_out_, (size_t)tot3 * std::max(D, E));
   const int nblk = S ? 0 : conv1_blocks_per_utt(maxT1);
   if (!S) gn_partial_.reserve((size_t)B * nblk * 2);
@@ -873,6 +954,25 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     launch_conv1_tanh(d_pcm, stride, d_ns, d_t1, d_off1, w1t_, h1_.ptr, D, B, maxT1, gn_partial_.ptr,
                       nullptr, stream_);
     stage("conv1", -1, 2);
+    if (conv_planes) {
+      // GroupNorm-apply writes conv2's im2col operand as plane tiles; conv2 (+bias+GELU) writes conv3's the same way in
+      // its epilogue; both convolutions are then plain plane-fed products -- no fp32 intermediate is stored at all.
+      unsigned char* a2 = reinterpret_cast<unsigned char*>(a2P_.ptr);
+      unsigned char* a3 = reinterpret_cast<unsigned char*>(a3P_.ptr);
+      launch_groupnorm_im2col_planes(h1_.ptr, d_t1, d_off1, gn_partial_.ptr, nblk, gn_w_, gn_b_, D, B, maxT1, a2, stream_);
+      stage("groupnorm", -1, 2);
+      GemmPlanesParams c2;
+      c2.A = a2; c2.W = conv2P_; c2.M = (int)tot2; c2.N = 2 * D; c2.K = 7 * D; c2.bias = conv2_b_; c2.act = 1;
+      c2.P = a3; c2.p_taps = 3; c2.p_stride = 2;
+      launch_gemm_planes(c2, stream_);
+      stage("conv2", -1, 2);
+      GemmPlanesParams c3;
+      c3.A = a3; c3.W = conv3P_; c3.M = (int)tot3; c3.N = D; c3.K = 6 * D; c3.bias = conv3_b_; c3.act = 1;
+      c3.C = x_.ptr; c3.ldc = D;
+      launch_gemm_planes(c3, stream_);
+      stage("conv3", -1, 2);
+      launches += 4;
+    } else {
     launch_groupnorm_apply(h1_.ptr, d_t1, d_off1, gn_partial_.ptr, nblk, gn_w_, gn_b_, D, B, maxT1, stream_);
     stage("groupnorm", -1, 2);
     launches += 2;
@@ -889,6 +989,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     launch_gemm(g3, stream_);
     stage("conv3", -1, 2);
     launches += 2;
+    }
   } else {
     // frames -> CMVN -> asinh (one warp per frame), then Linear(80 -> E) + SiLU as one GEMM over every
     // row of the padded layout: padding rows of `frames_` are zero and the linear has no bias, so the
@@ -926,8 +1027,23 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   }();
   for (int l = 0; l < d_.enc_layers; l++) {
     const EncLayer& w = enc_[l];
-    launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, E, stream_);
-    {  // Q|K projection (classic: with fused interleaved RoPE; the streaming encoder has no positions)
+    unsigned char* lnP = reinterpret_cast<unsigned char*>(lnP_.ptr);
+    unsigned char* attnP = reinterpret_cast<unsigned char*>(attnP_.ptr);
+    unsigned char* midP = reinterpret_cast<unsigned char*>(midP_.ptr);
+    if (enc_planes_) launch_layernorm_planes(x_.ptr, nullptr, lnP, w.ln1, tot3, E, stream_);
+    else launch_layernorm(x_.ptr, ln_.ptr, w.ln1, tot3, E, stream_);
+    if (enc_planes_) {
+      // Q | K | V in ONE product, both operands as pre-split planes (bulk copies feed the tensor core directly): columns
+      // < 2E land in the Q|K rows (with RoPE), columns >= 2E are stored transposed, V^T_b[e][t], as the attention wants them
+      GemmPlanesParams g;
+      g.A = lnP; g.W = w.wqkP; g.M = (int)tot3; g.N = 3 * E; g.K = E; g.C = qk_.ptr; g.ldc = 2 * E;
+      g.n_split = 2 * E; g.Vt = vt_.ptr; g.vt_row = d_vtrow; g.vt_ld = Tp;
+      if (!S) {
+        g.pos = d_pos; g.rope_cos = rope_cos_.ptr; g.rope_sin = rope_sin_.ptr;
+        g.rope_cols = 2 * E; g.head_dim = ehd; g.rot_dim = d_.rot_dim;
+      }
+      launch_gemm_planes(g, stream_);
+    } else {  // Q|K projection (classic: with fused interleaved RoPE; the streaming encoder has no positions)
       GemmParams g;
       g.A = ln_.ptr; g.lda = E; g.W = w.wqk; g.ldw = E; g.C = qk_.ptr; g.rs = 2 * E;
       g.M = (int)tot3; g.N = 2 * E; g.K = E;
@@ -937,7 +1053,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       }
       launch_gemm(g, stream_);
     }
-    {  // V^T_b[E, T_b] = Wv * ln_b^T  (swapped orientation, per utterance)
+    if (!enc_planes_) {  // V^T_b[E, T_b] = Wv * ln_b^T  (swapped orientation, per utterance)
       GemmParams g;
       g.A = w.wv; g.lda = E; g.strideA = 0; g.W = ln_.ptr; g.ldw = E; g.offW = d_offxb;
       g.C = vt_.ptr; g.offC = d_offvt; g.rs = Tp;
@@ -972,6 +1088,20 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
         launch_gemm(g, stream_);
       }
     }
+    if (enc_planes_) {
+      launch_rows_to_planes(attn_.ptr, E, tot3, E, attnP, stream_);
+      GemmPlanesParams o;  // x += attn Wo^T
+      o.A = attnP; o.W = w.woP; o.M = (int)tot3; o.N = E; o.K = E; o.C = x_.ptr; o.ldc = E; o.accumulate = 1;
+      launch_gemm_planes(o, stream_);
+      launch_layernorm_planes(x_.ptr, nullptr, lnP, w.ln2, tot3, E, stream_);
+      GemmPlanesParams f1;  // gelu(ln W1^T + b1), written straight as the planes fc2 reads
+      f1.A = lnP; f1.W = w.w1P; f1.M = (int)tot3; f1.N = EI; f1.K = E; f1.P = midP; f1.bias = w.b1; f1.act = 1;
+      launch_gemm_planes(f1, stream_);
+      GemmPlanesParams f2;  // x += mid W2^T + b2
+      f2.A = midP; f2.W = w.w2P; f2.M = (int)tot3; f2.N = E; f2.K = EI; f2.C = x_.ptr; f2.ldc = E; f2.bias = w.b2; f2.accumulate = 1;
+      launch_gemm_planes(f2, stream_);
+      launches += 1;
+    } else {
     {  // x += attn Wo^T
       GemmParams g;
       g.A = attn_.ptr; g.lda = E; g.W = w.wo; g.ldw = E; g.C = x_.ptr; g.rs = E;
@@ -988,6 +1118,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
       g2.A = mid_.ptr; g2.lda = EI; g2.W = w.w2; g2.ldw = EI; g2.C = x_.ptr; g2.rs = E;
       g2.M = (int)tot3; g2.N = E; g2.K = EI; g2.bias = w.b2; g2.accumulate = 1;
       launch_gemm(g2, stream_);
+    }
     }
     launches += 10;
     stage("encoder_layer", l, 4);

@@ -114,7 +114,9 @@ class Model {
  private:
   struct EncLayer {
     const float *ln1, *wqk, *wv, *wo, *ln2, *w1, *b1, *w2, *b2;
+    const unsigned char *wqkP, *woP, *w1P, *w2P;  // the dense weights as bf16 hi/lo plane tiles (gemm_planes.cu), or null
   };
+  bool enc_planes_ = false;  // encoder dense layers on the plane-fed tcgen05 GEMM
   void build_weights(const WeightFile& wf);
   void ensure_rope(int max_pos);
   struct AutoPlan {
@@ -163,6 +165,9 @@ class Model {
 
   // workspaces (grow-only)
   DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_, frames_;
+  DeviceBuffer<float> lnP_, attnP_, midP_, a2P_, a3P_;  // activations as plane tiles (byte buffers; sized in floats)
+  const unsigned char* conv2P_ = nullptr;  // conv2 / conv3 weights as plane tiles (classic frontend)
+  const unsigned char* conv3P_ = nullptr;
   DeviceBuffer<double> gn_partial_;
   DeviceBuffer<__half> kc_, vc_;
   DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_, xattn_dev_;
