@@ -687,7 +687,7 @@ int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, in
     GemmParams g;
     g.A = dA; g.W = dW; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.rs = ldc;
     g.bias = d_bias; g.act = act; g.accumulate = accumulate;
-    if (impl == 3 || impl == 4) {
+    if (impl >= 3 && impl <= 6) {  // 3 / 4: one tile per CTA, 5 / 6: persistent macro tiles; 4 and 6 also round-trip plane output
       // plane-fed kernel: both operands are converted to hi/lo plane tiles on the device first.  impl 4 also makes the
       // epilogue write the result as plane tiles and reads those back through a second plane-fed product with I_N.
       DeviceBuffer<float> pa, pw, pc;
@@ -699,12 +699,13 @@ int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, in
       GemmPlanesParams q;
       q.A = reinterpret_cast<unsigned char*>(pa.ptr); q.W = reinterpret_cast<unsigned char*>(pw.ptr);
       q.M = M; q.N = N; q.K = K; q.C = dC; q.ldc = ldc; q.bias = d_bias; q.act = act; q.accumulate = accumulate;
-      if (impl == 4) {
+      q.variant = impl >= 5 ? 2 : 1;
+      if (impl == 4 || impl == 6) {
         pc.reserve(plane_tiles_bytes(M, N) / 4);
         q.P = reinterpret_cast<unsigned char*>(pc.ptr);
       }
       launch_gemm_planes(q, nullptr);
-      if (impl == 4) {  // dC <- (planes of C) x I_N
+      if (impl == 4 || impl == 6) {  // dC <- (planes of C) x I_N
         DeviceBuffer<float> eye, pe;
         eye.reserve((size_t)N * N);
         CUDA_CHECK(cudaMemsetAsync(eye.ptr, 0, eye.bytes(), nullptr));
@@ -716,6 +717,7 @@ int32_t moonshine_b200_test_gemm(const float* dA, const float* dW, float* dC, in
         launch_rows_to_planes(eye.ptr, N, N, N, reinterpret_cast<unsigned char*>(pe.ptr), nullptr);
         GemmPlanesParams r;
         r.A = q.P; r.W = reinterpret_cast<unsigned char*>(pe.ptr); r.M = M; r.N = N; r.K = N; r.C = dC; r.ldc = ldc;
+        r.variant = q.variant;
         launch_gemm_planes(r, nullptr);
       }
       CUDA_CHECK(cudaDeviceSynchronize());

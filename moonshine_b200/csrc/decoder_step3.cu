@@ -1045,9 +1045,11 @@ __device__ void job_cross(const DecoderParams& p, int l, int job, Ctx& c, Ring& 
   const float scale = rsqrtf((float)hd);
   const int Tpad = p.Tpad;
   const int tpr = hd >> 2;           // threads per V row (4 halves = 8 bytes each)
-  // A tile of two utterances gives each utterance its own half of the CTA (4 warps, own named barrier and scratch);
-  // otherwise the whole CTA walks the utterances in turn.
-  const bool halves = (nb == 2) && (Tpad <= 512);
+  // Tiles with an even number of utterances give the two halves of the CTA (4 warps each, own named barrier and scratch)
+  // alternate utterances: while one half is in the softmax / PV of utterance b the other is already in the scores of
+  // b + 1 -- the 112 threads that own 4 keys each are all a 448-key utterance can use in the scores pass anyway.
+  // Otherwise (one utterance per tile) the whole CTA walks it.  MOONSHINE_B200_CROSS_HALVES=0 restores pairs-only.
+  const bool halves = (nb >= 2) && ((nb & 1) == 0) && (Tpad <= 512) && (nb == 2 || p.cross_halves);
   const int half = halves ? (int)(threadIdx.x >> 7) : 0;
   const int gtid = halves ? (int)(threadIdx.x & 127) : (int)threadIdx.x;
   const int gthreads = halves ? 128 : kConsumers;
@@ -1068,7 +1070,7 @@ __device__ void job_cross(const DecoderParams& p, int l, int job, Ctx& c, Ring& 
   float* pv = c.red + 32 + half * 512;      // [G][hd] PV partials (G * hd <= 1024, <= 512 per half)
   for (int b = 0; b < nb; b++) {
     if (c.flags[b]) continue;  // uniform
-    const bool mine = !halves || (b == half);  // every thread walks every chunk; only the owner group computes
+    const bool mine = !halves || ((b & 1) == half);  // every thread walks every chunk; only the owner group computes
     const int T = c.flags[32 + b];
     const float* q = c.act + b * actw;
     // ---- scores over K^T chunks (rows = head dims); group thread j owns t = 4j .. 4j+3 ----

@@ -19,8 +19,10 @@
 // Reference arithmetic: the encoder's q/k/o projections and MLP (HF MoonshineEncoderLayer; the ORT graphs the reference
 // runs, core/moonshine-model.cpp:185-262, hold the same fp32 contractions).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
+#include <string>
 
 #include "common.h"
 #include "kernels.h"
@@ -122,6 +124,107 @@ __device__ __forceinline__ void store_plane_row(unsigned char* planes, int nkb, 
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// one output row's 32 columns [n0, n0 + 32): bias / GELU / RoPE / residual accumulate, then whichever outputs are wanted.
+// (The epilogue is the critical resource of these short-K products -- 128 x 128 x 13 k-blocks of MMAs take ~3 us, a naive
+// epilogue longer -- so column -> (layer, head, dim) maps run on counters: one division per 32 columns, not per column.)
+__device__ __forceinline__ void epilogue_chunk(const GemmPlanesParams& p, int64_t m, int pos, int n0, float* v) {
+  const int ncols = min(32, p.N - n0);  // multiple of 4 (N % 4 == 0)
+  if (p.Hk != nullptr) {  // decoder cross K (time-contiguous) | V (head rows), fp16
+    if (n0 < p.n_split) {
+      const int64_t base = __ldg(p.hk_row + m);
+      if (base >= 0) {
+        int l = n0 / p.Dm, r = n0 - l * p.Dm;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          if (j < ncols) p.Hk[base + (int64_t)l * p.SL + (int64_t)r * p.Tpadm] = __float2half_rn(v[j]);
+          if (++r == p.Dm) { r = 0; l++; }
+        }
+      }
+    } else {
+      const int64_t base = __ldg(p.hv_row + m);
+      if (base >= 0) {
+        const int n = n0 - p.n_split;
+        int l = n / p.Dm, r = n - l * p.Dm, h = r / p.hdm, d = r - h * p.hdm;
+        const int64_t hs = (int64_t)p.Tpadm * p.hdm;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          if (j < ncols) p.Hv[base + (int64_t)l * p.SL + (int64_t)h * hs + d] = __float2half_rn(v[j]);
+          if (++d == p.hdm) {
+            d = 0;
+            if ((++h) * p.hdm == p.Dm) { h = 0; l++; }
+          }
+        }
+      }
+    }
+    return;
+  }
+  if (p.Vt != nullptr && n0 >= p.n_split) {
+    // transposed store: lanes of a warp hold consecutive rows = consecutive t of one utterance (mostly), so every
+    // column is one coalesced 128-byte line
+    const int64_t base = __ldg(p.vt_row + m);
+    if (base >= 0) {
+      float* dst = p.Vt + base + (int64_t)(n0 - p.n_split) * p.vt_ld;
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        if (j < ncols) dst[(int64_t)j * p.vt_ld] = v[j];
+    }
+    return;
+  }
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+      if (j < ncols) v[j] += __ldg(p.bias + n0 + j);
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = gelu_erf(v[j]);
+  }
+  if (p.pos != nullptr && n0 < p.rope_cols) {
+    // interleaved pairs (2i, 2i + 1) of the first rot_dim dims of every head; 32-column trips never split a pair
+    const int half_rot = p.rot_dim >> 1;
+    const float* cs_row = p.rope_cos + (int64_t)pos * half_rot;
+    const float* sn_row = p.rope_sin + (int64_t)pos * half_rot;
+    int d = n0 % p.head_dim;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      if (j < ncols && n0 + j < p.rope_cols && d < p.rot_dim) {
+        const float cs = __ldg(cs_row + (d >> 1)), sn = __ldg(sn_row + (d >> 1));
+        const float x0 = v[j], x1 = v[j + 1];
+        v[j] = x0 * cs - x1 * sn;
+        v[j + 1] = x1 * cs + x0 * sn;
+      }
+      d += 2;
+      if (d >= p.head_dim) d -= p.head_dim;
+    }
+  }
+  if (p.C != nullptr) {
+    float* dst = p.C + m * p.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(dst + j);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = o;
+        if (p.accumulate) { v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w; }
+      }
+    }
+  }
+  if (p.P != nullptr) {  // N % 32 == 0 (checked by the launcher)
+    const int nkb_out = p.N >> 5;
+    if (p.p_taps <= 1) {
+      store_plane_row(p.P, nkb_out, m, n0 >> 5, v);
+    } else {
+      // the output IS the next convolution's im2col operand: row r of that operand is p_taps consecutive output rows
+      // starting at p_stride * r, so output row m is tap k of row (m - k) / p_stride for every k congruent to m
+      for (int k = (int)(m % p.p_stride); k < p.p_taps; k += p.p_stride)
+        if (m >= k) store_plane_row(p.P, nkb_out * p.p_taps, (m - k) / p.p_stride, (k * p.N + n0) >> 5, v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128, 2) gemm_planes_kernel(const __grid_constant__ GemmPlanesParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // [kStages]
@@ -203,10 +306,8 @@ __global__ void __launch_bounds__(128, 2) gemm_planes_kernel(const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int64_t m = (int64_t)mt * 128 + warp * 32 + lane;
   const bool row_ok = m < p.M;
-  const int nkb_out = p.N >> 5;
   int pos = 0;
   if (p.pos != nullptr && row_ok) pos = p.pos[m];
-  const int half_rot = p.rot_dim >> 1;
 #pragma unroll 1
   for (int c = 0; c < 4; c++) {
     const int n0 = nt * 128 + c * 32;
@@ -229,73 +330,181 @@ __global__ void __launch_bounds__(128, 2) gemm_planes_kernel(const __grid_consta
       for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
     }
     if (!row_ok) continue;
-    const int ncols = min(32, p.N - n0);  // multiple of 4 (N % 4 == 0)
-    if (p.Vt != nullptr && n0 >= p.n_split) {
-      // transposed store: lanes of a warp hold consecutive rows = consecutive t of one utterance (mostly), so every
-      // column is one coalesced 128-byte line
-      const int64_t base = __ldg(p.vt_row + m);
-      if (base >= 0) {
-        float* dst = p.Vt + base + (int64_t)(n0 - p.n_split) * p.vt_ld;
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-          if (j < ncols) dst[(int64_t)j * p.vt_ld] = v[j];
-      }
-      continue;
-    }
-    if (p.bias != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; j++)
-        if (j < ncols) v[j] += __ldg(p.bias + n0 + j);
-    }
-    if (p.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = gelu_erf(v[j]);
-    }
-    if (p.pos != nullptr && n0 < p.rope_cols) {
-      // interleaved pairs (2i, 2i + 1) of the first rot_dim dims of every head; 32-column trips never split a pair
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const int n = n0 + j, d = n % p.head_dim;
-        if (j < ncols && n < p.rope_cols && d < p.rot_dim) {
-          const float cs = __ldg(p.rope_cos + (int64_t)pos * half_rot + (d >> 1));
-          const float sn = __ldg(p.rope_sin + (int64_t)pos * half_rot + (d >> 1));
-          const float x0 = v[j], x1 = v[j + 1];
-          v[j] = x0 * cs - x1 * sn;
-          v[j + 1] = x1 * cs + x0 * sn;
-        }
-      }
-    }
-    if (p.C != nullptr) {
-      float* dst = p.C + m * p.ldc + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(dst + j);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(dst + j) = o;
-          if (p.accumulate) { v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w; }
-        }
-      }
-    }
-    if (p.P != nullptr) {  // N % 32 == 0 (checked by the launcher)
-      if (p.p_taps <= 1) {
-        store_plane_row(p.P, nkb_out, m, n0 >> 5, v);
-      } else {
-        // the output IS the next convolution's im2col operand: row r of that operand is p_taps consecutive output rows
-        // starting at p_stride * r, so output row m is tap k of row (m - k) / p_stride for every k congruent to m
-        for (int k = (int)(m % p.p_stride); k < p.p_taps; k += p.p_stride)
-          if (m >= k) store_plane_row(p.P, nkb_out * p.p_taps, (m - k) / p.p_stride, (k * p.N + n0) >> 5, v);
-      }
-    }
+    epilogue_chunk(p, m, pos, n0, v);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+  }
+}
+
+// ---- tcgen05.ld of 32 accumulator columns of this warp's 32 rows ----
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent variant (default): one CTA per SM walks 128 x 256 macro tiles (one A tile against TWO adjacent W tiles, so
+// the activations cross L2 -> SM once per 256 output columns), stages of TWO k-blocks (32 KB bulk copies: a copy costs
+// ~0.45 us of its issuing thread whatever its size and an SM sustains ~4 copies / us, so 16 KB copies starve the tensor
+// core), and TWO 256-column TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i + 1.
+//   warp 0 / 1 / 3   bulk copies of A / W0 / W1          warp 2   MMA issue          warps 4-11   epilogue (2 per lane quarter)
+constexpr int kStages2 = 2;
+constexpr int kStage2 = 6 * kTile;  // 2 k-blocks x (A | W0 | W1)
+__global__ void __launch_bounds__(384, 1) gemm_planes_persistent_kernel(const __grid_constant__ GemmPlanesParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [2] 3 arrivals (A, W0, W1) + bytes
+  uint64_t* empty = full + kStages2;                     // [2] the MMA warp's commit
+  uint64_t* acc_full = empty + kStages2;                 // [2] accumulator b complete
+  uint64_t* acc_empty = acc_full + 2;                    // [2] accumulator b drained (8 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned char* ring = smem + 1024;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int nkb = p.K >> 5, nst = (nkb + 1) >> 1;
+  const int n_tiles = (p.N + 127) >> 7, n_macro = (n_tiles + 1) >> 1, m_tiles = (p.M + 127) >> 7;
+  const int total = n_macro * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; s++) {
+      mbar_init(&full[s], 3);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 || warp == 1 || warp == 3) {
+    // ---- producers: operand `which` (0 = A, 1 = W0, 2 = W1) of every stage of every tile of this CTA ----
+    const int which = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    int s = 0;
+    uint32_t par = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int mt = tile / n_macro, nm = tile - mt * n_macro;
+      const int rt = which == 0 ? mt : 2 * nm + (which - 1);      // row tile of the operand
+      const bool present = which == 0 || rt < n_tiles;            // the last macro tile may hold one W tile only
+      const unsigned char* src = (which == 0 ? p.A : p.W) + (int64_t)rt * nkb * kTile;
+      for (int st = 0; st < nst; st++) {
+        const uint32_t bytes = (uint32_t)min(2, nkb - 2 * st) * kTile;
+        mbar_wait(&empty[s], par ^ 1u);
+        __syncwarp();
+        if (elect_one()) {
+          if (present) {
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + s * kStage2 + which * 2 * kTile, src + (int64_t)st * 2 * kTile, bytes, &full[s]);
+          } else {
+            mbar_arrive(&full[s]);
+          }
+        }
+        __syncwarp();
+        if (++s == kStages2) { s = 0; par ^= 1u; }
+      }
+    }
+  } else if (warp == 2) {
+    // ---- MMA issue ----
+    int s = 0;
+    uint32_t par = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+      const int mt = tile / n_macro, nm = tile - mt * n_macro;
+      const bool two = 2 * nm + 1 < n_tiles;
+      const int b = it & 1;
+      mbar_wait(&acc_empty[b], ((uint32_t)(it >> 1) & 1u) ^ 1u);  // drained by the epilogue two tiles ago
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem + (uint32_t)(b * 256);
+      (void)mt;
+      for (int st = 0; st < nst; st++) {
+        const int nq = min(2, nkb - 2 * st);
+        mbar_wait(&full[s], par);
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = uniform_u32(smem_u32(ring + s * kStage2));
+        const uint32_t ebar = uniform_u32(smem_u32(&empty[s]));
+        if (elect_one()) {
+          for (int q = 0; q < nq; q++) {
+            const uint32_t a = base + (uint32_t)(q * kTile), w0 = base + (uint32_t)((2 + q) * kTile), w1 = base + (uint32_t)((4 + q) * kTile);
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {
+              const uint32_t ko = (uint32_t)ks * 32u;
+              const uint32_t first = (st | q | ks) ? 1u : 0u;
+              const uint64_t ahi = make_desc_sw64(a + ko), alo = make_desc_sw64(a + kTile / 2 + ko);
+              umma_bf16(acc, alo, make_desc_sw64(w0 + ko), kIdesc, first);
+              umma_bf16(acc, ahi, make_desc_sw64(w0 + kTile / 2 + ko), kIdesc, 1u);
+              umma_bf16(acc, ahi, make_desc_sw64(w0 + ko), kIdesc, 1u);
+              if (two) {
+                umma_bf16(acc + 128, alo, make_desc_sw64(w1 + ko), kIdesc, first);
+                umma_bf16(acc + 128, ahi, make_desc_sw64(w1 + kTile / 2 + ko), kIdesc, 1u);
+                umma_bf16(acc + 128, ahi, make_desc_sw64(w1 + ko), kIdesc, 1u);
+              }
+            }
+          }
+          umma_commit(ebar);
+        }
+        __syncwarp();
+        if (++s == kStages2) { s = 0; par ^= 1u; }
+      }
+      const uint32_t abar = uniform_u32(smem_u32(&acc_full[b]));
+      if (elect_one()) umma_commit(abar);
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps 4-11: TMEM lanes 32 (warp % 4) .. + 31, column half (warp - 4) / 4 of the macro tile ----
+    const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+      const int mt = tile / n_macro, nm = tile - mt * n_macro;
+      const int b = it & 1;
+      mbar_wait(&acc_full[b], (uint32_t)(it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t m = (int64_t)mt * 128 + ew * 32 + lane;
+      const bool row_ok = m < p.M;
+      int pos = 0;
+      if (p.pos != nullptr && row_ok) pos = p.pos[m];
+#pragma unroll 1
+      for (int c = half * 4; c < half * 4 + 4; c++) {
+        const int n0 = nm * 256 + c * 32;
+        if (n0 >= p.N) break;  // uniform
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * 256 + c * 32), v);
+        if (row_ok) epilogue_chunk(p, m, pos, n0, v);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
@@ -419,17 +628,43 @@ __global__ void rows_to_planes_kernel(const float* __restrict__ src, int64_t ld,
 bool gemm_planes_supported(const GemmPlanesParams& p) {
   return p.M > 0 && p.N > 0 && p.K >= 32 && p.K % 32 == 0 && p.N % 4 == 0 && (p.P == nullptr || p.N % 32 == 0) &&
          (p.Vt == nullptr || (p.n_split % 32 == 0 && p.vt_row != nullptr && p.P == nullptr)) &&
+         (p.Hk == nullptr || (p.Hv != nullptr && p.hk_row != nullptr && p.hv_row != nullptr && p.n_split % 32 == 0 && p.Vt == nullptr)) &&
          (p.p_taps <= 1 || (p.P != nullptr && p.p_stride >= 1 && p.p_stride <= p.p_taps)) &&
          (p.pos == nullptr || (p.head_dim % 2 == 0 && p.rot_dim % 2 == 0)) && (p.C == nullptr || p.ldc % 4 == 0);
 }
 
 void launch_gemm_planes(const GemmPlanesParams& p, cudaStream_t stream) {
   if (!gemm_planes_supported(p)) throw std::runtime_error("gemm_planes: unsupported shape");
-  const size_t smem = 1024 + (size_t)kStages * kStage;
-  static SmemAttrCache cache;
-  if (cache.needs(smem)) CUDA_CHECK(cudaFuncSetAttribute(gemm_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
-  gemm_planes_kernel<<<grid, 128, smem, stream>>>(p);
+  // Two mappings.  `tiles`: one 128 x 128 tile per CTA, 2 CTAs per SM -- best when a launch is only a few waves (tiny/32:
+  // 105 row tiles).  `persistent`: 128 x 256 macro tiles, epilogue overlapped -- best from ~8 macro tiles per SM on
+  // (base/256 encoder stage 27.2 -> 24.6 ms, base-streaming/64 7.0 -> 6.4; tiny/32 2.35 vs 2.49 the other way).
+  static const int forced = [] {
+    const char* e = std::getenv("MOONSHINE_B200_GEMM_PLANES");
+    return e == nullptr ? 0 : (std::string(e) == "tiles" ? 1 : (std::string(e) == "persistent" ? 2 : 0));
+  }();
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static int sm_count[64] = {0};
+  if (dev >= 0 && dev < 64) {
+    if (sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    sms = sm_count[dev] > 0 ? sm_count[dev] : 148;
+  }
+  const int n_macro = ((p.N + 127) / 128 + 1) / 2, m_tiles = (p.M + 127) / 128;
+  const int64_t total = (int64_t)n_macro * m_tiles;
+  const int want = p.variant ? p.variant : forced;
+  const bool tiles = want == 1 || (want == 0 && total < 8 * (int64_t)sms);
+  if (tiles) {
+    const size_t smem = 1024 + (size_t)kStages * kStage;
+    static SmemAttrCache cache;
+    if (cache.needs(smem)) CUDA_CHECK(cudaFuncSetAttribute(gemm_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
+    gemm_planes_kernel<<<grid, 128, smem, stream>>>(p);
+  } else {
+    const size_t smem = 1024 + (size_t)kStages2 * kStage2;
+    static SmemAttrCache cache;
+    if (cache.needs(smem)) CUDA_CHECK(cudaFuncSetAttribute(gemm_planes_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_planes_persistent_kernel<<<(unsigned)std::min<int64_t>(total, sms), 384, smem, stream>>>(p);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

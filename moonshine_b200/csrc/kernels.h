@@ -69,6 +69,7 @@ struct GemmPlanesParams {
   float* C = nullptr;                // fp32 output rows (row stride ldc), may be null when only planes are wanted
   int64_t ldc = 0;
   unsigned char* P = nullptr;        // optional: the output as planes of an [M][N] operand (input of the next GEMM)
+  int variant = 0;                   // 0 = pick by launch size, 1 = one 128 x 128 tile per CTA, 2 = persistent 128 x 256 macro tiles
   int p_taps = 1, p_stride = 1;      // > 1 taps: P is the im2col operand of a following convolution (row r = p_taps output rows from p_stride * r)
   const float* bias = nullptr;       // [N]
   int act = 0;                       // 1 = exact-erf GELU
@@ -79,6 +80,15 @@ struct GemmPlanesParams {
   int rope_cols = 0, head_dim = 1, rot_dim = 0;
   // optional column split: columns n >= n_split (a multiple of 32) are stored TRANSPOSED instead, Vt[vt_row[m] + (n - n_split) * vt_ld]
   // (rows with vt_row[m] < 0 are skipped) -- the encoder's V^T_b[e][t] next to its Q | K rows
+  // optional fp16 cross-K/V outputs of the decoder (replaces C / P): columns n < n_split = (l, h, d) of K, stored time-
+  // contiguous Hk[hk_row[m] + (n / Dm) * SL + (n % Dm) * Tpadm]; columns >= n_split = (l, h, d) of V,
+  // Hv[hv_row[m] + (n' / Dm) * SL + ((n' % Dm) / hdm) * Tpadm * hdm + n' % hdm]; rows with a negative base are skipped
+  __half* Hk = nullptr;
+  __half* Hv = nullptr;
+  const int64_t* hk_row = nullptr;
+  const int64_t* hv_row = nullptr;
+  int64_t SL = 0;
+  int Dm = 1, hdm = 1, Tpadm = 0;
   int n_split = 0;
   float* Vt = nullptr;
   const int64_t* vt_row = nullptr;
@@ -256,6 +266,7 @@ struct DecoderParams {
   // sparse logit bonuses added in the logits epilogue before the fused argmax (key-term biasing,
   // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
   int c4_cs, c4_nc, c4_u;     // v4: cluster size, clusters, utterances per cluster
+  int cross_halves;           // v3: the two halves of a CTA alternate the utterances of a cross-attention tile (default on)
   int pf_mask;                // L2 prefetch pipelines: v4 bit 0 weights, 1 cross K/V, 2 vocabulary slab; v3 bit 3 next-phase weights, 4 cross K/V window, 5 evict-first K/V
   // ---- explicit rows (v3 only; multi-token verify and per-utterance positions; reference: run_decoder_with_cross_kv
   // fed n > 1 tokens by decode_tokens / decode_full, core/moonshine-streaming-model.cpp:1136-1190, 1192-1397).  A row is

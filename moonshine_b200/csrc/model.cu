@@ -191,7 +191,7 @@ Model::Model(const Model& src, int device) : d_(src.d_), device_(device) {
   };
   w1t_ = rb(src.w1t_); gn_w_ = rb(src.gn_w_); gn_b_ = rb(src.gn_b_);
   conv2_w_ = rb(src.conv2_w_); conv2_b_ = rb(src.conv2_b_); conv3_w_ = rb(src.conv3_w_); conv3_b_ = rb(src.conv3_b_);
-  conv2P_ = rbb(src.conv2P_); conv3P_ = rbb(src.conv3P_);
+  conv2P_ = rbb(src.conv2P_); conv3P_ = rbb(src.conv3P_); wkvP_ = rbb(src.wkvP_);
   enc_final_ln_ = rb(src.enc_final_ln_);
   s_lin_w_ = rb(src.s_lin_w_); s_c1_w_ = rb(src.s_c1_w_); s_c1_b_ = rb(src.s_c1_b_); s_c2_w_ = rb(src.s_c2_w_); s_c2_b_ = rb(src.s_c2_b_);
   pos_emb_ = rb(src.pos_emb_); proj_w_ = rb(src.proj_w_);
@@ -344,6 +344,7 @@ void Model::build_weights(const WeightFile& wf) {
     const int Ee = d_.streaming ? d_.enc_dim : D, EIe = d_.streaming ? d_.enc_ffn : I;
     enc_planes_ = Ee % 32 == 0 && EIe % 32 == 0 && Ee <= 512;
     if (const char* e = std::getenv("MOONSHINE_B200_ENC")) enc_planes_ = enc_planes_ && std::string(e) != "classic";
+    // (the decoder's stacked cross K | V projections [2 L D][D] are packed after the decoder weights are laid out)
     if (enc_planes_ && !d_.streaming) {  // conv2 [2D][7D] and conv3 [D][6D] (tap-major K, as the fp32 copies)
       const size_t c2 = o_c2, c3 = o_c3;
       o_conv2P = pack_tile_planes(bb, 2 * D, 7 * D, [&](int n, int k) { return bb.data[c2 + (size_t)n * 7 * D + k]; });
@@ -577,6 +578,13 @@ void Model::build_weights(const WeightFile& wf) {
     std::memcpy(&bb.data[o_wk_all + (size_t)l * D * D], kc, sizeof(float) * D * D);
     std::memcpy(&bb.data[o_wv_all + (size_t)l * D * D], vc, sizeof(float) * D * D);
   }
+  size_t o_wkvP = 0;
+  if (enc_planes_ && D % 32 == 0) {  // every layer's cross K then every layer's cross V projection as plane tiles: ONE product
+    const int LD = d_.dec_layers * D;
+    o_wkvP = pack_tile_planes(bb, 2 * LD, D, [&](int n, int k) {
+      return n < LD ? bb.data[o_wk_all + (size_t)n * D + k] : bb.data[o_wv_all + (size_t)(n - LD) * D + k];
+    });
+  }
 
   wblob_.reserve(bb.data.size());
   CUDA_CHECK(cudaMemcpyAsync(wblob_.ptr, bb.data.data(), bb.data.size() * sizeof(float),
@@ -609,6 +617,7 @@ void Model::build_weights(const WeightFile& wf) {
   enc_final_ln_ = base + o_encln;
   wk_all_ = base + o_wk_all;
   wv_all_ = base + o_wv_all;
+  wkvP_ = (enc_planes_ && D % 32 == 0) ? reinterpret_cast<const unsigned char*>(base) + o_wkvP * 4 : nullptr;
   std::memset(&dec_, 0, sizeof(dec_));
   dec_.D = D; dec_.H = H; dec_.hd = hd; dec_.I = I; dec_.V = V; dec_.L = d_.dec_layers;
   dec_.rot_dim = d_.rot_dim; dec_.IC = IC; dec_.n_chunk = n_chunk; dec_.ffn_ksplit = ffn_ksplit_;
@@ -616,6 +625,8 @@ void Model::build_weights(const WeightFile& wf) {
   {
     const char* e = std::getenv("MOONSHINE_B200_PREFETCH");  // experiment knob (bit mask, see DecoderParams::pf_mask); default 32 = evict-first hint on v3's cross K/V stream (base/256 1677 -> 1582 us/step, base-streaming/64 842 -> 776); the prefetch bits measured neutral or negative (profiles/r2e_prefetch_ab.txt)
     dec_.pf_mask = e ? std::atoi(e) : 32;
+    const char* ch = std::getenv("MOONSHINE_B200_CROSS_HALVES");
+    dec_.cross_halves = !(ch && ch[0] == '0');
   }
   dec_.embed = base + o_emb; dec_.embT = base + o_embT; dec_.final_ln = base + o_decln;
   dec_.embP = base + o_embP; dec_.vchunk = vchunk_; dec_.n_vchunk = n_vchunk_; dec_.smem_limit = smem_optin_;
@@ -834,7 +845,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   // int64: off1[B] offQ[BH] offK[BH] offS[BH] offVh[BH] offO[BH] offXb[B] offVt[B] offKc[B] offVc[B]
   //        offMem[B] frRow[B] c1A[B] c1C[B] c2A[B] c2C[B]
   const size_t n_i32 = (size_t)4 * B + tot3 + BH + B + 3 * B;
-  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B + 6 * B + (size_t)tot3;  // + vtRow[tot3]: V^T address of every packed row (-1: padding row)
+  const size_t n_i64 = (size_t)B + 5 * BH + 4 * B + 6 * B + 3 * (size_t)tot3;  // + vtRow | kcRow | vcRow [tot3]: output address of every packed row (-1: skip)
   pin_i32_.reserve(n_i32);
   pin_i64_.reserve(n_i64);
   meta_i32_.reserve(n_i32);
@@ -852,7 +863,8 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   int64_t *h_offmem = h_offvc + B, *h_frrow = h_offmem + B, *h_c1a = h_frrow + B, *h_c1c = h_c1a + B,
           *h_c2a = h_c1c + B, *h_c2c = h_c2a + B;
   int64_t* h_vtrow = h_c2c + B;
-  for (int64_t r = 0; r < tot3; r++) h_vtrow[r] = -1;
+  int64_t *h_kcrow = h_vtrow + tot3, *h_vcrow = h_kcrow + tot3;
+  for (int64_t r = 0; r < 3 * tot3; r++) h_vtrow[r] = -1;
   std::memset(h_pos, 0, sizeof(int) * tot3);
   for (int b = 0; b < B; b++) {
     h_ns[b] = nsamp[b]; h_t1[b] = T1[b]; h_t3[b] = T3[b]; h_ml[b] = mlen[b];
@@ -862,6 +874,10 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     for (int t = 0; t < T3[b]; t++) {
       h_pos[r3 + t] = t;
       h_vtrow[r3 + t] = (int64_t)b * E * Tp + t;
+      if (t < Tm[b]) {  // decoder memory rows: cross K^T [L][B][H][hd][Tpad] / V [L][B][H][Tpad][hd]
+        h_kcrow[r3 + t] = (int64_t)b * H * hd * Tpad + t;
+        h_vcrow[r3 + t] = (int64_t)b * H * Tpad * hd + (int64_t)t * hd;
+      }
     }
     h_dzb[b] = E;
     h_offxb[b] = r3 * E;
@@ -897,6 +913,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   const int64_t *d_offmem = d_offvc + B, *d_frrow = d_offmem + B, *d_c1a = d_frrow + B, *d_c1c = d_c1a + B,
                 *d_c2a = d_c1c + B, *d_c2c = d_c2a + B;
   const int64_t* d_vtrow = d_c2c + B;
+  const int64_t *d_kcrow = d_vtrow + tot3, *d_vcrow = d_kcrow + tot3;
 
   // ---------------- workspaces ----------------
   auto reserve_zero = [&](DeviceBuffer<float>& buf, size_t n) {
@@ -1168,7 +1185,20 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     vc_.reserve(kv_elems);
   }
   CUDA_CHECK(cudaMemsetAsync(kc_.ptr, 0, kv_elems * sizeof(__half), stream_));
-  {
+  if (wkvP_ != nullptr) {
+    // one plane-fed product for every layer's cross K and V: memory rows x [Wk_0 .. Wk_L-1 | Wv_0 .. Wv_L-1]^T, the
+    // epilogue stores fp16 straight into the step kernels' layouts (K time-contiguous, V as head rows)
+    reserve_zero(encP_, plane_tiles_bytes(tot3, D) / 4);
+    unsigned char* encP = reinterpret_cast<unsigned char*>(encP_.ptr);
+    launch_rows_to_planes(enc_out_.ptr, D, tot3, D, encP, stream_);
+    GemmPlanesParams g;
+    g.A = encP; g.W = wkvP_; g.M = (int)tot3; g.N = 2 * L * D; g.K = D;
+    g.Hk = kc_.ptr; g.Hv = vc_.ptr; g.hk_row = d_kcrow; g.hv_row = d_vcrow; g.n_split = L * D;
+    g.SL = (int64_t)B * H * hd * Tpad; g.Dm = D; g.hdm = hd; g.Tpadm = Tpad;
+    launch_gemm_planes(g, stream_);
+    launches += 2;
+    stage("cross_kv", -1, 8);
+  } else {
     GemmParams g;  // K^T: rows (l, h, d), cols t
     g.A = wk_all_; g.lda = D; g.W = enc_out_.ptr; g.ldw = D; g.offW = d_offmem;
     g.C = kc_.ptr; g.offC = d_offkc; g.out_half = 1;

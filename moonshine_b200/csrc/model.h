@@ -165,9 +165,10 @@ class Model {
 
   // workspaces (grow-only)
   DeviceBuffer<float> pcm_dev_, h1_, h2_, x_, ln_, qk_, vt_, scores_, attn_, mid_, enc_out_, frames_;
-  DeviceBuffer<float> lnP_, attnP_, midP_, a2P_, a3P_;  // activations as plane tiles (byte buffers; sized in floats)
+  DeviceBuffer<float> lnP_, attnP_, midP_, a2P_, a3P_, encP_;  // activations as plane tiles (byte buffers; sized in floats)
   const unsigned char* conv2P_ = nullptr;  // conv2 / conv3 weights as plane tiles (classic frontend)
   const unsigned char* conv3P_ = nullptr;
+  const unsigned char* wkvP_ = nullptr;    // stacked cross K | V projections of every decoder layer as plane tiles
   DeviceBuffer<double> gn_partial_;
   DeviceBuffer<__half> kc_, vc_;
   DeviceBuffer<float> ks_, vs_, hbuf_, part_, xfin_, cand_val_, logits_dbg_, xattn_dev_;

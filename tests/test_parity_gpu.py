@@ -276,17 +276,17 @@ def test_gemm_kernel_against_torch(impl, tol):
         assert (C2 - ref2).abs().max().item() / ref2.abs().max().item() < tol
 
 
-@pytest.mark.parametrize("impl", [3, 4], ids=["planes", "planes_out_roundtrip"])
+@pytest.mark.parametrize("impl", [3, 4, 5, 6], ids=["tiles", "tiles_planes_out", "persistent", "persistent_planes_out"])
 def test_plane_fed_gemm_against_torch(impl):
     """gemm_planes.cu (both operands pre-split to bf16 hi/lo plane tiles, bulk-copy fed tcgen05) against float64: bias +
-    exact GELU, accumulate, ragged M / N.  impl 4 also writes the result as plane tiles (the fc1 -> fc2 hand-over) and
+    exact GELU, accumulate, ragged M / N, both CTA mappings (one tile per CTA / persistent macro tiles).  impl 4 / 6 also write the result as plane tiles (the fc1 -> fc2 hand-over) and
     reads it back through a second plane-fed product with the identity: hi + lo carries ~16 mantissa bits."""
     import torch
     lib = api.load_library()
     torch.manual_seed(0)
     shapes = [(300, 200, 64), (129, 256, 32), (1000, 576, 288), (415, 416, 416), (128, 128, 32), (77, 1152, 288), (2049, 288, 1152)]
     for (M, N, K) in shapes:
-        if impl == 4 and N % 32:
+        if impl in (4, 6) and N % 32:
             continue
         A = torch.randn(M, K, device="cuda")
         W = torch.randn(N, K, device="cuda")
@@ -296,8 +296,8 @@ def test_plane_fed_gemm_against_torch(impl):
         assert rc == 0
         ref = torch.nn.functional.gelu(A.double() @ W.double().T + bias.double()).float()
         err = (C - ref).abs().max().item() / ref.abs().max().item()
-        assert err < (6e-5 if impl == 3 else 1e-4), (M, N, K, err)
-        if impl == 3:
+        assert err < (6e-5 if impl in (3, 5) else 1e-4), (M, N, K, err)
+        if impl in (3, 5):
             C2 = torch.ones(M, N, device="cuda")
             rc = lib.moonshine_b200_test_gemm(A.data_ptr(), W.data_ptr(), C2.data_ptr(), M, N, K, K, K, N, 0, 0, 1, impl)
             assert rc == 0

@@ -33,6 +33,26 @@ def content(ids, d):
     return [i for i in ids if i not in (d.bos, d.eos)]
 
 
+def assert_same_ids_up_to_near_ties(t, arch, audios, want, got, label):
+    """The verify path and the greedy path run the same fp32 arithmetic in different orders (other tile shapes, other kernels),
+    so the two may part ways -- but only AT a position where the model's own top-2 candidates are tied to within rounding
+    (the reference has a tool that counts exactly these, core/speculative-mismatch-investigate.cpp).  Past such a position
+    the contexts differ and that utterance is no longer comparable."""
+    d = ARCHS[arch]
+    for u, (w, g) in enumerate(zip(want, got)):
+        if w == g:
+            continue
+        i = next((k for k in range(min(len(w), len(g))) if w[k] != g[k]), None)
+        assert i is not None and i >= 1, (label, u, "one list is a strict prefix of the other", w, g)
+        forced = np.zeros((len(audios), max(len(x) for x in want) + 1), np.int32)
+        for k, x in enumerate(want):
+            forced[k, :len(x)] = x
+        _, lg, _ = t.debug_run(audios, d.dim, d.vocab, forced=forced, logits_steps=i, want_encoder=False, max_tokens=300)
+        row = lg[i - 1, u]
+        gap = abs(float(row[w[i]]) - float(row[g[i]])) / float(np.abs(row).max())
+        assert gap < 2e-5, (label, u, i, w[i], g[i], gap)
+
+
 @pytest.mark.parametrize("arch", ["test", "test_streaming", "tiny_streaming"])
 def test_any_draft_gives_the_greedy_ids(arch):
     d = ARCHS[arch]
@@ -54,7 +74,7 @@ def test_any_draft_gives_the_greedy_ids(arch):
     launches = {}
     for name, drafts in cases.items():
         got, launches[name] = t.decode_with_drafts(audios, drafts, max_tokens=300)
-        assert got == want, name
+        assert_same_ids_up_to_near_ties(t, arch, audios, want, got, name)
     longest = max(len(w) for w in want) - 1          # ids the longest utterance emits
     assert launches["empty"] >= longest              # no draft: the plain greedy loop, one launch per id
     assert launches["exact"] <= (longest + 1 + 7) // 8 + 2, launches   # the whole draft in ceil((m+1)/8) launches (+ the tail)
