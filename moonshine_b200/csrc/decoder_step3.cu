@@ -98,32 +98,29 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// A wait that runs out of patience poisons the grid (error flag) instead of trapping the context.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* err) {
-  const uint32_t a = smem_u32(bar);
-  if (mbar_try(a, parity)) return;
+// A wait that runs out of patience poisons the grid (error flag) instead of trapping the context.  Only the first try is
+// inlined: the kernel is several times the 128 KB instruction cache, and every inlined spin loop made that worse.
+__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity, unsigned* err, int nap) {
   const long long t0 = clock64();
   unsigned polls = 0;
   while (!mbar_try(a, parity)) {
+    if (nap) __nanosleep(32);
     if ((++polls & 15u) == 0u) {
       if (poisoned(err)) return;
       if (clock64() - t0 > kSpinLimit) { atomicExch(err, 1u); return; }
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* err) {
+  const uint32_t a = smem_u32(bar);
+  if (mbar_try(a, parity)) return;
+  mbar_wait_slow(a, parity, err, 0);
+}
 // Same wait for threads that are NOT on the critical path: back off between polls.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned* err) {
   const uint32_t a = smem_u32(bar);
   if (mbar_try(a, parity)) return;
-  const long long t0 = clock64();
-  unsigned polls = 0;
-  while (!mbar_try(a, parity)) {
-    __nanosleep(32);
-    if ((++polls & 15u) == 0u) {
-      if (poisoned(err)) return;
-      if (clock64() - t0 > kSpinLimit) { atomicExch(err, 1u); return; }
-    }
-  }
+  mbar_wait_slow(a, parity, err, 1);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -142,13 +139,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {  // bytes: multiple of 16
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// this CTA's 1/G share of a block, in 16 KB pieces (`piece` runs on across the blocks of one call site)
-__device__ __forceinline__ void l2_prefetch_share(const void* src, size_t bytes, int& piece) {
-  const int G = (int)gridDim.x, me = (int)blockIdx.x;
-  for (size_t o = 0; o < bytes; o += 16384, piece++)
-    if (piece % G == me) l2_prefetch(reinterpret_cast<const char*>(src) + o, (uint32_t)min((size_t)16384, bytes - o));
-}
-
 // ---- tcgen05 helpers ----
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -869,23 +859,23 @@ __device__ void job_self(const DecoderParams& p, int l, int job, Ctx& c, Ring& r
       const float* Kt = p.ks + bh * hd * p.Smax;
       const float* Vr = p.vs + bh * p.Smax * hd;
       float mx = -INFINITY;
-      // scores: two key positions per lane, 12 head dims per trip = 24 independent loads in flight per lane (the
+      // scores: two key positions per lane, 32 head dims per trip = 64 independent loads in flight per lane (the
       // chain is memory-latency bound: the prefix was written by earlier launches and has left L2 since)
       for (int t0 = 0; t0 < base; t0 += 64) {
         const int ta = t0 + lane, tb = t0 + 32 + lane;
         const bool va = ta < base, vb = tb < base;
         float sa = 0.f, sb = 0.f;
 #pragma unroll 1
-        for (int d0 = 0; d0 < hd; d0 += 12) {
-          float ka[12], kb[12];
+        for (int d0 = 0; d0 < hd; d0 += 32) {  // 64 loads in flight per lane: hd <= 64 is two round trips, not six
+          float ka[32], kb[32];
 #pragma unroll
-          for (int u = 0; u < 12; u++) {
+          for (int u = 0; u < 32; u++) {
             const bool in = d0 + u < hd;
             ka[u] = (va && in) ? __ldg(Kt + (int64_t)(d0 + u) * p.Smax + ta) : 0.f;
             kb[u] = (vb && in) ? __ldg(Kt + (int64_t)(d0 + u) * p.Smax + tb) : 0.f;
           }
 #pragma unroll
-          for (int u = 0; u < 12; u++) {
+          for (int u = 0; u < 32; u++) {
             const float qd = d0 + u < hd ? q[d0 + u] : 0.f;
             sa = fmaf(qd, ka[u], sa);
             sb = fmaf(qd, kb[u], sb);
@@ -987,26 +977,13 @@ __device__ __forceinline__ void produce_cross(const DecoderParams& p, int l, int
   const int h = job % H, b0 = (job / H) * nb;
   if (!tile_active(p, active, nb, b0)) return;
   const DecLayerWeights& w = p.layers[l];
-  // The ring alone keeps ~4 x 32 KB in flight per SM: at HBM latency under load that is ~25 GB/s per SM, a third of
-  // what 128 streaming CTAs need to fill HBM.  A sliding window of L2 prefetches (kCrossWindow utterances ahead of the
-  // ring) multiplies the bytes in flight; the ring copies then hit L2 and mark the lines evict-first on the way out,
-  // so the 191 MB a layer streams does not push the next phase's (prefetched) weights out of L2.
-  constexpr int kCrossWindow = 3;
-  const uint32_t kv_bytes = (uint32_t)(hd * p.Tpad * 2);
-  const bool window = (p.pf_mask & 16) != 0 && ring.turn == 0;  // one of the producer lanes (fixed for the whole job)
+  // The cross K/V stream carries an L2 evict-first hint: the 191 MB a base/256 layer streams must not push the weight
+  // planes out of L2 (measured 1677 -> 1582 us/step; an L2 prefetch window ahead of the ring and next-phase weight
+  // prefetches were built and measured neutral or negative, profiles/r2e_prefetch_ab.txt, and removed again).
   uint64_t pol = 0;
   if (p.pf_mask & 32) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  auto ask = [&](int b) {
-    if (b >= nb || b0 + b >= p.B || !active[b0 + b]) return;
-    const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
-    l2_prefetch(p.kc + bh * hd * p.Tpad, kv_bytes);
-    l2_prefetch(p.vc + bh * p.Tpad * hd, kv_bytes);
-  };
-  if (window)
-    for (int b = 0; b < kCrossWindow; b++) ask(b);
   produce_block_planes(ring, w.wqcP + (size_t)h * plane_block_bytes(hd, D), hd, D);
   for (int b = 0; b < nb; b++) {
-    if (window) ask(b + kCrossWindow);
     if (b0 + b >= p.B || !active[b0 + b]) continue;
     const int64_t bh = ((int64_t)l * cache_utts(p) + row_utterance(p, b0 + b)) * H + h;
     produce_block_f16(ring, p.kc + bh * hd * p.Tpad, hd, p.Tpad, pol);   // K^T [hd][Tpad]
@@ -1589,23 +1566,6 @@ __global__ void __launch_bounds__(kThreads3, 1) decoder_step3_kernel(const __gri
         const int l = pi / kPhasesPerLayer;
         const int kind = l < p.L ? pi - l * kPhasesPerLayer : PH_FINAL + (pi - p.L * kPhasesPerLayer);
         if (kind == PH_FINAL) continue;  // no ring traffic
-        // Next phase's weight blocks -> L2, this CTA's 1/G share (the producer runs a ring ahead of the consumers, so
-        // this is issued roughly one phase before the blocks are asked for by every CTA that shares them at once).
-        if ((p.pf_mask & 8) && (threadIdx.x - kConsumers) < 32) {
-          int piece = 0;
-          const DecLayerWeights& w = p.layers[l < p.L ? l : 0];
-          if (kind == PH_LOGITS) {  // the next launch's first blocks (the weights do not change between steps)
-            l2_prefetch_share(w.wqkvP, (size_t)p.H * plane_block_bytes(3 * p.hd, p.D), piece);
-            l2_prefetch_share(w.wo, (size_t)p.D * p.D * 4, piece);
-          } else if (kind == PH_SELF) l2_prefetch_share(w.wqcP, (size_t)p.H * plane_block_bytes(p.hd, p.D), piece);
-          else if (kind == PH_CROSS) l2_prefetch_share(w.wocF, plane_block_bytes(p.D, p.D), piece);
-          else if (kind == PH_OC) l2_prefetch_share(w.w1iF, plane_block_bytes(2 * p.I, p.D), piece);
-          else if (kind == PH_FC1) l2_prefetch_share(w.w2kF, (size_t)p.ffn_ksplit * plane_block_bytes(p.D, p.I / p.ffn_ksplit), piece);
-          else if (kind == PH_FC2 && l + 1 < p.L) {
-            l2_prefetch_share(p.layers[l + 1].wqkvP, (size_t)p.H * plane_block_bytes(3 * p.hd, p.D), piece);
-            l2_prefetch_share(p.layers[l + 1].wo, (size_t)p.D * p.D * 4, piece);
-          }
-        }
         const int njobs = phase_jobs(p, kind);
         int j0, stride;
         my_jobs(p, kind, njobs, j0, stride);

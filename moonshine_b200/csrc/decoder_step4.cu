@@ -599,52 +599,9 @@ __global__ void __launch_bounds__(kThreads4, 1) decoder_step4_kernel(const __gri
       PCur pc;
       const int pidx = (threadIdx.x - kConsumers) >> 5;
       pc.st = 0; pc.par = 0; pc.turn = pidx;
-      // L2 prefetch pipeline.  All clusters walk the layers in lockstep, so a weight chunk asked for by the ring is
-      // asked for by every cluster within the same microsecond: the first request misses to HBM and the others queue on
-      // the same fill, i.e. every ring copy pays HBM latency and the ring (bytes in flight / latency) starves the dense
-      // routine.  Instead the producers ask L2 for the NEXT layer's operands one layer ahead: each cluster prefetches a
-      // 1/NC share of the weight pieces of its ranks' slices (the union over clusters is every slice), its own cross K/V,
-      // and -- halfway through the layers -- its share of the vocabulary slab; the ring copies then hit L2.
-      const int nca = (p.B + U - 1) / U;  // clusters that hold utterances
-      auto pf_weights = [&](int l) {
-        if (!(p.pf_mask & 1) || cid >= nca) return;
-        const DecLayerWeights& w = p.layers[l];
-        const void* ptr[6] = {w.wqkv + (int64_t)hh * D * 3 * hd, w.c4_wo + (int64_t)rank * D * dsp, w.wqc + (int64_t)hh * D * hd,
-                              w.c4_woc + (int64_t)rank * D * dsp, w.c4_w1 + (int64_t)rank * D * 2 * is, w.c4_w2 + (int64_t)rank * is * D};
-        const uint32_t len[6] = {(uint32_t)(D * 3 * hd * 4), (uint32_t)(D * dsp * 4), (uint32_t)(D * hd * 4),
-                                 (uint32_t)(D * dsp * 4), (uint32_t)(D * 2 * is * 4), (uint32_t)(is * D * 4)};
-        int piece = 0;
-        for (int i = 0; i < 6; i++)
-          for (uint32_t o = 0; o < len[i]; o += 16384, piece++)
-            if (piece % nca == cid) l2_prefetch(reinterpret_cast<const char*>(ptr[i]) + o, min(16384u, len[i] - o));
-      };
-      auto pf_cross = [&](int l) {
-        if (!(p.pf_mask & 2)) return;
-        for (int u = sub; u < nu; u += RH) {
-          if (!active[u]) continue;
-          const int64_t bh = ((int64_t)l * p.B + (u0 + u)) * H + hh;
-          l2_prefetch(p.kc + bh * hd * p.Tpad, (uint32_t)(hd * p.Tpad * 2));
-          l2_prefetch(p.vc + bh * p.Tpad * hd, (uint32_t)(hd * p.Tpad * 2));
-        }
-      };
-      auto pf_slab = [&]() {
-        if (!(p.pf_mask & 4)) return;
-        const size_t item_bytes = (size_t)p.vchunk * D * 4;
-        for (int item = (int)blockIdx.x; item < n_vjobs; item += G) {
-          const char* slab = reinterpret_cast<const char*>(p.embP) + (size_t)item * item_bytes;
-          for (size_t o = 0; o < item_bytes; o += 32768) l2_prefetch(slab + o, (uint32_t)min((size_t)32768, item_bytes - o));
-        }
-      };
-      if (pidx == 0) pf_weights(0);
       if (any_active) {
-        if (pidx == kProducers - 1) pf_cross(0);
         for (int l = 0; l < p.L; l++) {
           const DecLayerWeights& w = p.layers[l];
-          if (pidx == 0) pf_weights(l + 1 < p.L ? l + 1 : 0);  // the last layer asks for layer 0 of the next launch
-          if (pidx == kProducers - 1) {
-            if (l + 1 < p.L) pf_cross(l + 1);
-            if (l == p.L / 2) pf_slab();
-          }
           produce_f32(ring, pc, w.wqkv + (int64_t)hh * D * 3 * hd, D, 3 * hd, pol_keep);
           if (p.step > 0 && pc.turn == 0) {  // self K/V prefix of this rank's items: ask L2 for it a stage ahead
             for (int u = sub; u < nu; u += RH) {

@@ -267,7 +267,7 @@ struct DecoderParams {
   // reference: ContextBiaser::apply, core/context-biaser.cpp:88-132); all null = no biasing
   int c4_cs, c4_nc, c4_u;     // v4: cluster size, clusters, utterances per cluster
   int cross_halves;           // v3: the two halves of a CTA alternate the utterances of a cross-attention tile (default on)
-  int pf_mask;                // L2 prefetch pipelines: v4 bit 0 weights, 1 cross K/V, 2 vocabulary slab; v3 bit 3 next-phase weights, 4 cross K/V window, 5 evict-first K/V
+  int pf_mask;                // bit 5 (32): L2 evict-first hint on the v3 cross K/V stream (the L2 prefetch experiments of round 2 -- bits 0-4 -- measured neutral or negative and were removed, profiles/r2e_prefetch_ab.txt)
   // ---- explicit rows (v3 only; multi-token verify and per-utterance positions; reference: run_decoder_with_cross_kv
   // fed n > 1 tokens by decode_tokens / decode_full, core/moonshine-streaming-model.cpp:1136-1190, 1192-1397).  A row is
   // one (utterance, position) pair; rows of one utterance are consecutive, ascending in position, and never straddle a
