@@ -1,6 +1,10 @@
 // Host orchestration of the batched encoder and the greedy decoder.
 #include "model.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <chrono>
@@ -699,6 +703,40 @@ const StreamPlan* Model::auto_plan(const uint64_t*& n_samples, int B, float max_
   return &ap.plan;
 }
 
+// Staging copy with non-temporal stores: a DMA engine reading lines that are still dirty in the CPU caches has to snoop
+// them out (measured here: 20 MB staged by 16 cores then copied host-to-device at ~9 GB/s instead of the 54 GB/s the same
+// link gives for data that sits in DRAM); streaming stores put the staged audio straight into memory.  dst 16-byte aligned.
+static void stream_copy(float* dst, const float* src, size_t n) {
+#if defined(__SSE2__)
+  size_t i = 0;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    for (; i + 16 <= n; i += 16) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 4));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 8));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 12));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 8), c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 12), d);
+    }
+    _mm_sfence();
+  }
+  if (i < n) std::memcpy(dst + i, src + i, (n - i) * sizeof(float));
+#else
+  std::memcpy(dst, src, n * sizeof(float));
+#endif
+}
+
+static bool nt_stores() {
+  static const bool on = [] { const char* e = std::getenv("MOONSHINE_B200_STAGE_NT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int stage_mode() {  // experiment knob MOONSHINE_B200_STAGE: 0 threads + per-slice DMA, 1 pool + per-slice DMA, 2 pool + one DMA
+  static const int m = [] { const char* e = std::getenv("MOONSHINE_B200_STAGE"); return e ? std::atoi(e) : 2; }();
+  return m;
+}
+
 void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B, float max_tps,
                        std::vector<std::vector<int32_t>>& tokens, DebugCapture* dbg, const StreamPlan* plan,
                        std::vector<CrossAttention>* xattn, LogitHook* hook) {
@@ -715,21 +753,32 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
   const auto t0 = std::chrono::steady_clock::now();
   for (int b = 0; b < B; b++)
     if (pcm[b] == nullptr && n_samples[b] > 0) throw std::runtime_error("Audio data is nullptr");
-  // Stage through pinned memory and start each slice's DMA as soon as it is staged.  Large batches
-  // split the staging over a few host threads (one memcpy thread moves ~5 GB/s, PCIe 5 x16 ~50).
+  // Stage through pinned memory on the persistent worker pool (one memcpy thread moves ~5 GB/s, PCIe 5 x16 ~50) and start
+  // each slice's DMA as soon as it is staged: rows of a slice are contiguous in both buffers, the DMAs are issued in order
+  // by this thread as the slices complete.
   {
     const size_t total_bytes = (size_t)B * stride * sizeof(float);
-    const int nthreads = total_bytes < ((size_t)2 << 20) ? 1 : std::min(8, B);
-    auto stage_rows = [&](int lo, int hi) {
-      for (int b = lo; b < hi; b++)
-        std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
-    };
-    if (nthreads == 1) {
-      stage_rows(0, B);
+    if (total_bytes < ((size_t)2 << 20) || B < 2) {
+      for (int b = 0; b < B; b++) std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
       CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr, pin_pcm_.ptr, total_bytes, cudaMemcpyHostToDevice, stream_));
-    } else {
-      // rows [lo, hi) of a slice are contiguous in both buffers: one DMA per slice, issued in order
-      // by this thread as the slices complete
+    } else if (stage_mode() == 2) {
+      // stage everything on the pool, then ONE DMA (a copy engine reading lines other cores are still writing is slow)
+      const int n_slices = std::min(B, 16);
+      const int per = (B + n_slices - 1) / n_slices;
+      WorkerPool::instance().parallel_for(n_slices, [&](int i) {
+        const int lo = i * per, hi = std::min(B, lo + per);
+        for (int b = lo; b < hi; b++) {
+          if (nt_stores()) stream_copy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], (size_t)n_samples[b]);
+          else std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+        }
+      });
+      CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr, pin_pcm_.ptr, total_bytes, cudaMemcpyHostToDevice, stream_));
+    } else if (stage_mode() == 0) {
+      const int nthreads = std::min(8, B);
+      auto stage_rows = [&](int lo, int hi) {
+        for (int b = lo; b < hi; b++)
+          std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+      };
       std::vector<std::thread> pool;
       std::vector<std::pair<int, int>> slices;
       const int per = (B + nthreads - 1) / nthreads;
@@ -742,6 +791,38 @@ void Model::transcribe(const float* const* pcm, const uint64_t* n_samples, int B
         CUDA_CHECK(cudaMemcpyAsync(pcm_dev_.ptr + off, pin_pcm_.ptr + off, cnt * sizeof(float),
                                    cudaMemcpyHostToDevice, stream_));
       }
+    } else {
+      const int n_slices = std::min(B, 16);
+      const int per = (B + n_slices - 1) / n_slices;
+      std::vector<std::atomic<int>> ready(n_slices);
+      for (auto& r : ready) r.store(0);
+      std::exception_ptr dma_error;
+      std::atomic<int> issued{0};
+      std::mutex issue_mu;
+      // whoever finishes slice i tries to issue every DMA whose predecessors are all staged (in order, one issuer at a time)
+      auto issue_ready = [&]() {
+        std::lock_guard<std::mutex> lock(issue_mu);
+        while (issued.load() < n_slices && ready[issued.load()].load()) {
+          const int i = issued.load();
+          const int lo = i * per, hi = std::min(B, lo + per);
+          if (lo < hi && !dma_error) {
+            const size_t off = (size_t)lo * stride, cnt = (size_t)(hi - lo) * stride;
+            if (cudaMemcpyAsync(pcm_dev_.ptr + off, pin_pcm_.ptr + off, cnt * sizeof(float), cudaMemcpyHostToDevice, stream_) != cudaSuccess)
+              dma_error = std::make_exception_ptr(std::runtime_error("host-to-device copy of the staged audio failed"));
+          }
+          issued.fetch_add(1);
+        }
+      };
+      const int dev = device_;
+      WorkerPool::instance().parallel_for(n_slices, [&](int i) {
+        const int lo = i * per, hi = std::min(B, lo + per);
+        for (int b = lo; b < hi; b++)
+          std::memcpy(pin_pcm_.ptr + (size_t)b * stride, pcm[b], n_samples[b] * sizeof(float));
+        ready[i].store(1);
+        cudaSetDevice(dev);  // pool threads issue DMAs on this model's device
+        issue_ready();
+      });
+      if (dma_error) std::rethrow_exception(dma_error);
     }
   }
   const auto t1 = std::chrono::steady_clock::now();
@@ -850,7 +931,10 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   pin_i64_.reserve(n_i64);
   meta_i32_.reserve(n_i32);
   meta_i64_.reserve(n_i64);
+  static const bool host_prof = std::getenv("MOONSHINE_B200_HOST_PROF") != nullptr;
+  const auto hp0 = std::chrono::steady_clock::now();
   CUDA_CHECK(cudaStreamSynchronize(stream_));  // previous call may still read pinned staging
+  const auto hp1 = std::chrono::steady_clock::now();
   int* pi = pin_i32_.ptr;
   int64_t* pl = pin_i64_.ptr;
   int *h_ns = pi, *h_t1 = pi + B, *h_t3 = pi + 2 * B, *h_ml = pi + 3 * B, *h_pos = pi + 4 * B;
@@ -965,6 +1049,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   CUDA_CHECK(cudaMemsetAsync(vt_.ptr, 0, (size_t)B * E * Tp * sizeof(float), stream_));
 
   stage("setup", -1, 1);
+  const auto hp2 = std::chrono::steady_clock::now();
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
   // ---------------- frontend ----------------
   if (!S) {
@@ -1214,6 +1299,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
     launches += 2;
     stage("cross_kv", -1, 8);
   }
+  const auto hp3 = std::chrono::steady_clock::now();
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
 
   // ---------------- greedy decode ----------------
@@ -1600,6 +1686,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   times_.decode_launches = steps_launched + 1;
   times_.decoder_version = use_v4 ? 4 : use_v3 ? 3 : use_v2 ? 2 : 1;
   launches += steps_launched + 1;
+  const auto hp4 = std::chrono::steady_clock::now();
   if (timing_) CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
 
   // ---------------- results ----------------
@@ -1611,6 +1698,12 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   *h_err = 0u;
   if (use_v3) CUDA_CHECK(cudaMemcpyAsync(h_err, sync3_.ptr + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (host_prof) {
+    const auto hp5 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    MSB_LOGF("host profile: run(): entry sync %.2f ms, metadata + workspaces %.2f, enqueue frontend..cross-kv %.2f, enqueue decode %.2f, wait for the GPU %.2f",
+             ms(hp0, hp1), ms(hp1, hp2), ms(hp2, hp3), ms(hp3, hp4), ms(hp4, hp5));
+  }
   if (*h_err != 0u)
     throw std::runtime_error("decoder step watchdog: a wait inside the persistent kernel exceeded its limit "
                              "(results discarded; the device context is intact)");

@@ -651,29 +651,12 @@ void Transcriber::transcribe_batch(const float* const* audio, const uint64_t* le
     batch_outputs_.push_back(std::make_unique<TranscriptOutput>());
     vads.push_back(make_segmenter());
   }
-  // utterances are independent: resample + segment them on a few host threads
-  {
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, count / 2));
-    auto work = [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; i++) {
-        vads[i]->start();
-        vads[i]->process_audio(audio[i], (size_t)lengths[i], sample_rate, /*last_call=*/true);
-        vads[i]->stop();
-      }
-    };
-    if (nthreads <= 1) {
-      work(0, count);
-    } else {
-      std::vector<std::thread> pool;
-      const uint64_t per = (count + nthreads - 1) / nthreads;
-      for (unsigned t = 0; t < nthreads; t++) {
-        const uint64_t lo = t * per, hi = std::min<uint64_t>(count, lo + per);
-        if (lo < hi) pool.emplace_back(work, lo, hi);
-      }
-      for (auto& th : pool) th.join();
-    }
-  }
+  // utterances are independent: resample + segment them on the persistent worker pool
+  WorkerPool::instance().parallel_for((int)count, [&](int i) {
+    vads[i]->start();
+    vads[i]->process_audio(audio[i], (size_t)lengths[i], sample_rate, /*last_call=*/true);
+    vads[i]->stop();
+  });
   const auto tp1 = std::chrono::steady_clock::now();
   for (uint64_t i = 0; i < count; i++)
     jobs.push_back(Job{batch_outputs_[i].get(), &vads[i]->segments(), true});
