@@ -382,7 +382,7 @@ def main():
             "configs": configs, "published_reference": PUBLISHED,
             "clocks": summarise_clocks(clock_lines, local), "wall_s_headline": wall_head,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed beside the N = 1 line only
             threads = host_threads()
             try:
                 r = hf_arm(model, audios[:3], audios[:min(B, 16)], threads)
