@@ -248,6 +248,9 @@ MOONSHINE_EXPORT int32_t moonshine_b200_decode_with_drafts(
 MOONSHINE_EXPORT int32_t moonshine_b200_decode_tokens(
     int32_t transcriber_handle, const float *const *audio, const uint64_t *lengths, uint64_t count,
     const int32_t *tokens, int32_t tokens_stride, int32_t n_steps, int32_t rows_per_launch, float *logits_out);
+/* Host-only self-test of the persistent worker pool behind the batch path (segmentation, staging): returns 0 when every
+   item of every parallel_for ran exactly once under `callers` concurrent callers and an exception reached its caller. */
+MOONSHINE_EXPORT int32_t moonshine_b200_debug_pool_selftest(int32_t callers, int32_t n, int32_t rounds);
 /* Parity hook for the streaming architectures: when enabled, moonshine_b200_debug_run /
    moonshine_b200_transcribe_device treat each utterance as a NON-final update of its segment
    (the encoder's look-ahead features are held back, core/moonshine-streaming-model.cpp:624-626). */

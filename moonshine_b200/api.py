@@ -107,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "moonshine_free_grapheme_to_phonemizer", "moonshine_text_to_phonemes",
     "moonshine_transcribe_batch_without_streaming", "moonshine_b200_transcribe_device",
     "moonshine_b200_get_stream", "moonshine_b200_set_timing", "moonshine_b200_last_timings",
-    "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial", "moonshine_b200_decode_with_drafts", "moonshine_b200_decode_tokens",
+    "moonshine_b200_debug_run", "moonshine_b200_debug_stream_partial", "moonshine_b200_decode_with_drafts", "moonshine_b200_decode_tokens", "moonshine_b200_debug_pool_selftest",
     "moonshine_b200_debug_tokens_to_text", "moonshine_b200_debug_resample", "moonshine_b200_debug_align_words", "moonshine_b200_test_ring_bandwidth",
     "moonshine_b200_debug_text_to_tokens", "moonshine_b200_debug_biaser_apply", "moonshine_b200_debug_biaser_apply_sparse", "moonshine_b200_debug_extract_terms", "moonshine_b200_test_gemm",
 ]
@@ -206,6 +206,8 @@ def load_library() -> ctypes.CDLL:
     lib.moonshine_b200_decode_with_drafts.restype = c.c_int32
     lib.moonshine_b200_decode_with_drafts.argtypes = [
         c.c_int32, c.POINTER(f32p), u64p, c.c_uint64, i32p, c.c_int32, i32p, i32p, c.c_int32, i32p, i32p]
+    lib.moonshine_b200_debug_pool_selftest.restype = c.c_int32
+    lib.moonshine_b200_debug_pool_selftest.argtypes = [c.c_int32, c.c_int32, c.c_int32]
     lib.moonshine_b200_decode_tokens.restype = c.c_int32
     lib.moonshine_b200_decode_tokens.argtypes = [
         c.c_int32, c.POINTER(f32p), u64p, c.c_uint64, i32p, c.c_int32, c.c_int32, c.c_int32, f32p]

@@ -10,6 +10,9 @@
 #include <set>
 
 #include <cuda_runtime.h>
+
+#include <atomic>
+#include <thread>
 #include "../../include/moonshine_b200.h"
 #include "transcriber.h"
 #include "word_alignment.h"
@@ -534,6 +537,41 @@ int32_t moonshine_b200_decode_tokens(int32_t transcriber_handle, const float* co
     return MOONSHINE_ERROR_UNKNOWN;
   }
   return MOONSHINE_ERROR_NONE;
+}
+
+// Self-test of the persistent host worker pool (no GPU): `callers` threads each run parallel_for over `n` items `rounds`
+// times and check every item ran exactly once; one extra round throws from an item and must surface in the caller.
+// Returns 0 when everything held.
+int32_t moonshine_b200_debug_pool_selftest(int32_t callers, int32_t n, int32_t rounds) {
+  try {
+    std::atomic<int> bad{0};
+    std::vector<std::thread> ts;
+    for (int c = 0; c < callers; c++) {
+      ts.emplace_back([&]() {
+        std::vector<std::atomic<int>> hits(n);
+        for (int r = 0; r < rounds; r++) {
+          for (auto& h : hits) h.store(0);
+          WorkerPool::instance().parallel_for(n, [&](int i) { hits[i].fetch_add(1); });
+          for (int i = 0; i < n; i++)
+            if (hits[i].load() != 1) bad.fetch_add(1);
+        }
+        bool thrown = false;
+        try {
+          WorkerPool::instance().parallel_for(n, [&](int i) {
+            if (i == n / 2) throw std::runtime_error("item failed");
+          });
+        } catch (const std::runtime_error&) {
+          thrown = true;
+        }
+        if (!thrown && n > 0) bad.fetch_add(1);
+      });
+    }
+    for (auto& t : ts) t.join();
+    return bad.load();
+  } catch (const std::exception& e) {
+    MSB_LOGF("pool selftest failed: %s", e.what());
+    return -1;
+  }
 }
 
 // ---- host-only parity hooks (no GPU needed): the product's own helpers, callable from the CPU tests that

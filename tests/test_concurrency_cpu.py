@@ -56,3 +56,12 @@ def test_streams_and_one_shot_calls_from_many_threads():
         th.join()
     t.close()
     assert not errors, errors
+
+
+def test_worker_pool_runs_every_item_once_and_propagates_exceptions():
+    """The persistent pool behind the batch path (segmentation of a batch, staging copies): several callers at once, odd
+    item counts, an exception thrown by one item reaches its own caller and nobody else."""
+    from moonshine_b200 import api
+    lib = api.load_library()
+    for callers, n, rounds in [(1, 1, 3), (1, 37, 20), (4, 257, 10), (8, 16, 50), (3, 1000, 5)]:
+        assert lib.moonshine_b200_debug_pool_selftest(callers, n, rounds) == 0, (callers, n, rounds)
