@@ -17,9 +17,9 @@ cap() {  # name regex model batch [skip]
 }
 cap decoder4_tiny_b32 decoder_step4_kernel tiny 32 30
 cap decoder3_base_b256 decoder_step3_kernel base 256 30
-cap gemm_tc_tiny_b32 gemm_tc_kernel tiny 32 0
+cap gemm_tc_bs64 gemm_tc_kernel base_streaming 64 1
 cap gemm_planes_fc1_tiny_b32 gemm_planes_kernel tiny 32 4
-cap gemm_planes_fc1_base_b256 gemm_planes_kernel base 256 4
+cap gemm_planes_persistent_fc1_base_b256 gemm_planes_persistent_kernel base 256 4
 cap layernorm_planes_tiny_b32 layernorm_planes_kernel tiny 32 2
 cap groupnorm_im2col_tiny_b32 groupnorm_im2col_planes_kernel tiny 32 0
 cap attention_tc_tiny_b32 attention_tc_kernel tiny 32 2
