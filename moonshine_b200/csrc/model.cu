@@ -933,7 +933,11 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   meta_i64_.reserve(n_i64);
   static const bool host_prof = std::getenv("MOONSHINE_B200_HOST_PROF") != nullptr;
   const auto hp0 = std::chrono::steady_clock::now();
-  CUDA_CHECK(cudaStreamSynchronize(stream_));  // previous call may still read pinned staging
+  // The pinned metadata below is rewritten by every call.  A call that ran to its end has synchronised the stream (its
+  // results were read back), so nothing can still be reading it; only a call that left early (exception) forces a wait.
+  // Not waiting here lets the metadata build and the first launches overlap this call's own audio DMA.
+  if (stream_dirty_) CUDA_CHECK(cudaStreamSynchronize(stream_));
+  stream_dirty_ = true;
   const auto hp1 = std::chrono::steady_clock::now();
   int* pi = pin_i32_.ptr;
   int64_t* pl = pin_i64_.ptr;
@@ -1260,6 +1264,8 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   }
   if (dbg && dbg->skip_decode) {
     tokens.assign(B, std::vector<int32_t>());
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    stream_dirty_ = false;
     return;
   }
 
@@ -1698,6 +1704,7 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   *h_err = 0u;
   if (use_v3) CUDA_CHECK(cudaMemcpyAsync(h_err, sync3_.ptr + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
+  stream_dirty_ = false;
   if (host_prof) {
     const auto hp5 = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

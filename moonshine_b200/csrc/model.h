@@ -136,6 +136,7 @@ class Model {
   cudaStream_t stream_ = nullptr;
   bool timing_ = false;
   bool debug_stream_partial_ = false;
+  bool stream_dirty_ = false;  // a run() left work on the stream without the closing synchronise (exception path)
   StageTimes times_;
   cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
