@@ -218,7 +218,7 @@ MOONSHINE_EXPORT int32_t moonshine_b200_transcribe_device(
 /* cudaStream_t the transcriber launches on (for CUDA-event timing). */
 MOONSHINE_EXPORT void *moonshine_b200_get_stream(int32_t transcriber_handle);
 /* Enables per-stage CUDA-event timing; out[0..7] = frontend_ms, encoder_ms,
-   cross_kv_ms, decode_ms, decode_steps, kernel_launches, weight_bytes, 0. */
+   cross_kv_ms, decode_ms, decode_steps, kernel_launches, weight_bytes, decoder kernel version (1-4). */
 MOONSHINE_EXPORT int32_t moonshine_b200_set_timing(int32_t transcriber_handle, int32_t enabled);
 MOONSHINE_EXPORT int32_t moonshine_b200_last_timings(int32_t transcriber_handle, double *out8);
 /* Parity hook: runs host PCM utterances and returns intermediate tensors.
