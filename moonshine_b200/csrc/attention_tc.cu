@@ -37,6 +37,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ unsigned int g_attention_error = 0;  // watchdog flag (see attention_tc_error_async)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
@@ -50,7 +51,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > kSpinLimit) __trap();
+    if (clock64() - t0 > kSpinLimit) {  // poison instead of trapping the context: the host raises after its next synchronise
+      atomicExch(&g_attention_error, 1u);
+      break;
+    }
   }
 }
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
@@ -466,6 +470,14 @@ void launch_attention_tc(const AttnParams& p, int groups, int max_t, cudaStream_
     CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((max_t + 127) / 128, groups);
   attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
+}
+
+void attention_tc_error_async(unsigned int* pinned_dst, cudaStream_t stream) {
+  CUDA_CHECK(cudaMemcpyFromSymbolAsync(pinned_dst, g_attention_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, stream));
+}
+void attention_tc_clear_error(cudaStream_t stream) {
+  const unsigned int zero = 0;
+  CUDA_CHECK(cudaMemcpyToSymbolAsync(g_attention_error, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, stream));
 }
 
 }  // namespace msb

@@ -53,12 +53,21 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// A wait that runs out of patience (a lost copy) poisons the launch instead of trapping the context: the flag makes every
+// later wait of the grid return at once, the kernel drains with garbage, and the host turns the flag into an exception
+// after its next synchronise (gemm_planes_take_error) -- the device context stays usable.
+__device__ unsigned int g_planes_error = 0;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   if (mbar_try(a, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try(a, parity))
-    if (clock64() - t0 > kSpin) __trap();  // a lost copy: fail the launch instead of hanging the device
+  unsigned polls = 0;
+  while (!mbar_try(a, parity)) {
+    if ((++polls & 63u) == 0u) {
+      if (*reinterpret_cast<volatile unsigned int*>(&g_planes_error) != 0u) return;
+      if (clock64() - t0 > kSpin) { atomicExch(&g_planes_error, 1u); return; }
+    }
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -666,6 +675,14 @@ void launch_gemm_planes(const GemmPlanesParams& p, cudaStream_t stream) {
     gemm_planes_persistent_kernel<<<(unsigned)std::min<int64_t>(total, sms), 384, smem, stream>>>(p);
   }
   CUDA_CHECK(cudaGetLastError());
+}
+
+void gemm_planes_error_async(unsigned int* pinned_dst, cudaStream_t stream) {
+  CUDA_CHECK(cudaMemcpyFromSymbolAsync(pinned_dst, g_planes_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, stream));
+}
+void gemm_planes_clear_error(cudaStream_t stream) {
+  const unsigned int zero = 0;
+  CUDA_CHECK(cudaMemcpyToSymbolAsync(g_planes_error, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, stream));
 }
 
 void launch_layernorm_planes(const float* x, float* y, unsigned char* planes, const float* gamma, int64_t rows, int D,

@@ -46,6 +46,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ unsigned int g_gemm_tc_error = 0;  // watchdog flag (see gemm_tc_error_async)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
@@ -59,7 +60,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > kSpinLimitTC) __trap();
+    if (clock64() - t0 > kSpinLimitTC) {  // poison instead of trapping the context: the host raises after its next synchronise
+      atomicExch(&g_gemm_tc_error, 1u);
+      break;
+    }
   }
 }
 
@@ -342,6 +346,14 @@ void launch_gemm(const GemmParams& p, cudaStream_t stream) {
   }();
   if (use_simt) launch_gemm_simt(p, stream);
   else launch_gemm_tc(p, stream);
+}
+
+void gemm_tc_error_async(unsigned int* pinned_dst, cudaStream_t stream) {
+  CUDA_CHECK(cudaMemcpyFromSymbolAsync(pinned_dst, g_gemm_tc_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, stream));
+}
+void gemm_tc_clear_error(cudaStream_t stream) {
+  const unsigned int zero = 0;
+  CUDA_CHECK(cudaMemcpyToSymbolAsync(g_gemm_tc_error, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, stream));
 }
 
 }  // namespace msb

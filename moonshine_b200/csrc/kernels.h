@@ -96,6 +96,13 @@ struct GemmPlanesParams {
 };
 bool gemm_planes_supported(const GemmPlanesParams& p);
 void launch_gemm_planes(const GemmPlanesParams& p, cudaStream_t stream);
+// watchdog flag of the plane-fed kernels (a wait that timed out): copy it to pinned memory in stream order / reset it
+void gemm_planes_error_async(unsigned int* pinned_dst, cudaStream_t stream);
+void gemm_planes_clear_error(cudaStream_t stream);
+void gemm_tc_error_async(unsigned int* pinned_dst, cudaStream_t stream);
+void gemm_tc_clear_error(cudaStream_t stream);
+void attention_tc_error_async(unsigned int* pinned_dst, cudaStream_t stream);
+void attention_tc_clear_error(cudaStream_t stream);
 // y (optional fp32 rows) and planes of LayerNorm(x) * gamma
 void launch_layernorm_planes(const float* x, float* y, unsigned char* planes, const float* gamma, int64_t rows, int D,
                              cudaStream_t stream);

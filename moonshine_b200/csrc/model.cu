@@ -1703,8 +1703,25 @@ void Model::run(const float* d_pcm, int64_t stride, const uint64_t* n_samples, i
   unsigned* h_err = reinterpret_cast<unsigned*>(hn + B + 1);  // spare word behind the counts and the n_active staging word
   *h_err = 0u;
   if (use_v3) CUDA_CHECK(cudaMemcpyAsync(h_err, sync3_.ptr + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
+  // watchdog flags of the tcgen05 kernels outside the decoder step (plane-fed GEMM, fp32-staged GEMM, fused attention): a
+  // wait that ran out of patience poisons its launch instead of trapping the context; raised here, after the synchronise
+  unsigned* h_wd = reinterpret_cast<unsigned*>(hn + 2 * B + 1);
+  h_wd[0] = h_wd[1] = h_wd[2] = 0u;
+  gemm_planes_error_async(h_wd, stream_);
+  gemm_tc_error_async(h_wd + 1, stream_);
+  attention_tc_error_async(h_wd + 2, stream_);
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   stream_dirty_ = false;
+  if (h_wd[0] | h_wd[1] | h_wd[2]) {
+    const unsigned which = h_wd[0] ? 0u : (h_wd[1] ? 1u : 2u);
+    gemm_planes_clear_error(stream_);
+    gemm_tc_clear_error(stream_);
+    attention_tc_clear_error(stream_);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    static const char* names[3] = {"plane-fed GEMM", "fp32-staged GEMM", "fused attention"};
+    throw std::runtime_error(std::string(names[which]) + " watchdog: a wait inside the kernel exceeded its limit "
+                             "(results discarded; the device context is intact)");
+  }
   if (host_prof) {
     const auto hp5 = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
